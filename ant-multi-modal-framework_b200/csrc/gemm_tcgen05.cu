@@ -1,0 +1,390 @@
+// b200mm — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = epilogue(alpha * A[M,K] · B[N,K]^T)      bf16 operands, fp32 accumulation in TMEM
+//
+// Replaces nn.Linear / matmul on the ViT+BERT path (see include/b200mm.h for the reference call sites) in
+// forward (A=x, B=W), dgrad (A=dY, B=W read MN-major) and wgrad (A=dY, B=x, both MN-major) form, so no operand
+// is ever transposed through HBM.
+//
+// Structure (one CTA per SM, 256 threads, static round-robin tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D boxes into a 4-stage 128B-swizzled smem ring
+//   warp 1      MMA issuer: one lane issues tcgen05.mma 128x256x16 (SS operands), accumulators in TMEM,
+//               tcgen05.commit releases smem stages and publishes finished accumulators
+//   warp 2      TMEM allocator (512 columns = 2 accumulator stages of 256 fp32 columns)
+//   warps 4..7  epilogue: tcgen05.ld 32 columns at a time -> bias/activation/residual -> 16B global stores;
+//               runs concurrently with the next tile's mainloop thanks to the double-buffered accumulator
+#include "common.cuh"
+
+#include <stdlib.h>
+
+namespace b200mm {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = one 128B swizzle row
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SLAB_BYTES = 64 * BK * 2;  // MN-major operands arrive as 64(mn) x 64(k) slabs of 8 KB
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // +1024: manual 1 KB alignment of the ring
+constexpr uint32_t TMEM_COLS = 512;
+
+struct EpiParams {
+  void* D;
+  int64_t ldd;
+  int32_t d_f32;
+  float alpha;
+  const __nv_bfloat16* bias;
+  int32_t act;
+  __nv_bfloat16* aux_out;
+  const __nv_bfloat16* dact_in;
+  int64_t ld_dact;
+  const __nv_bfloat16* residual;
+  int64_t ldr;
+};
+
+struct GemmParams {
+  int64_t M, N, K;
+  int32_t m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  float* partial;  // split-K: f32 [splits][M][N]; nullptr when splits == 1
+  uint32_t mn_lbo, mn_sbo, k_lbo, k_sbo;  // descriptor byte offsets (defaults below; env-overridable for bring-up)
+  EpiParams epi;
+};
+
+// Full epilogue on 8 consecutive columns of one row (n % 8 == 0). Shared by the GEMM epilogue warps and the split-K
+// reduction kernel.
+__device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, const EpiParams& e) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= e.alpha;
+  if (e.bias != nullptr) {
+    uint4 b = *reinterpret_cast<const uint4*>(e.bias + n);
+    float2 f0 = unpack_bf16x2(b.x), f1 = unpack_bf16x2(b.y), f2 = unpack_bf16x2(b.z), f3 = unpack_bf16x2(b.w);
+    v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+    v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+  }
+  if (e.aux_out != nullptr) {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(e.aux_out + m * e.ldd + n) = o;
+  }
+  if (e.dact_in != nullptr) {
+    uint4 u = *reinterpret_cast<const uint4*>(e.dact_in + m * e.ld_dact + n);
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    float x[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= apply_dact(e.act, x[j]);
+  } else if (e.act != B200MM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(e.act, v[j]);
+  }
+  if (e.residual != nullptr) {
+    uint4 r = *reinterpret_cast<const uint4*>(e.residual + m * e.ldr + n);
+    float2 f0 = unpack_bf16x2(r.x), f1 = unpack_bf16x2(r.y), f2 = unpack_bf16x2(r.z), f3 = unpack_bf16x2(r.w);
+    v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+    v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+  }
+  if (e.d_f32) {
+    float* d = reinterpret_cast<float*>(e.D) + m * e.ldd + n;
+    *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + m * e.ldd + n) = o;
+  }
+}
+
+struct TileCoord {
+  int32_t m_blk, n_blk, split, kb0, kb1;
+};
+__device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p) {
+  TileCoord c;
+  int64_t per_split = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  c.split = static_cast<int32_t>(t / per_split);
+  int64_t rem = t - c.split * per_split;
+  c.m_blk = static_cast<int32_t>(rem / p.n_tiles);
+  c.n_blk = static_cast<int32_t>(rem - static_cast<int64_t>(c.m_blk) * p.n_tiles);
+  c.kb0 = c.split * p.kb_per_split;
+  c.kb1 = min(p.kb_total, c.kb0 + p.kb_per_split);
+  return c;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(t, p);
+      const int32_t m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
+      for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          const int32_t k0 = kb * BK;
+          if constexpr (!A_MN) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int s = 0; s < BM / 64; ++s) tma_load_2d(&tmA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int s = 0; s < BN / 64; ++s) tma_load_2d(&tmB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(t, p);
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 k-elements = 32 B inside the 128B swizzle row; 8-row groups 1024 B apart (SBO).
+            // MN-major: 16 k-rows = 2048 B; 8-k-row groups 1024 B apart (SBO); 64-wide mn slabs 8 KB apart (LBO).
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, p.mn_lbo, p.mn_sbo)
+                                        : make_smem_desc_sw128(a_base + k * 32, p.k_lbo, p.k_sbo);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, p.mn_lbo, p.mn_sbo)
+                                        : make_smem_desc_sw128(b_base + k * 32, p.k_lbo, p.k_sbo);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(t, p);
+      const int64_t m = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32 + lane;
+      const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (m < p.M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int64_t n = n0 + c * 32 + g * 8;
+            if (n < p.N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              if (p.partial != nullptr) {
+                float* d = p.partial + (static_cast<int64_t>(tc.split) * p.M + m) * p.N + n;
+                *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                epi_apply8(v, m, n, p.epi);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// split-K reduction + full epilogue; one thread per 8 output columns
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __restrict__ partial, int64_t M, int64_t N,
+                                                                  int32_t splits, EpiParams e) {
+  const int64_t n8 = N / 8;
+  const int64_t total = M * n8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = i / n8;
+    const int64_t n = (i - m * n8) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < splits; ++s) {
+      const float* src = partial + (static_cast<int64_t>(s) * M + m) * N + n;
+      float4 a = *reinterpret_cast<const float4*>(src);
+      float4 b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+      v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    epi_apply8(v, m, n, e);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+  static bool attr_set = false;  // benign race: idempotent attribute
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm smem=%d): %s", GEMM_SMEM_BYTES, cudaGetErrorString(e));
+      return B200MM_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int grid = static_cast<int>(total_tiles < sm_count() ? total_tiles : sm_count());
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace b200mm
+
+using namespace b200mm;
+
+extern "C" int64_t b200mm_gemm_workspace_bytes(int64_t M, int64_t N, int32_t splits) {
+  return splits > 1 ? static_cast<int64_t>(splits) * M * N * 4 : 0;
+}
+
+extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200MM_REQUIRE(a != nullptr, B200MM_ERR_SHAPE, "gemm: null args");
+  B200MM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, B200MM_ERR_SHAPE, "gemm: M=%lld N=%lld K=%lld must be positive",
+                 (long long)a->M, (long long)a->N, (long long)a->K);
+  B200MM_REQUIRE(a->N % 8 == 0, B200MM_ERR_SHAPE, "gemm: N=%lld must be a multiple of 8", (long long)a->N);
+  B200MM_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), B200MM_ERR_SHAPE, "gemm: dims exceed int32");
+  B200MM_REQUIRE(a->A && a->B && a->D, B200MM_ERR_SHAPE, "gemm: null operand");
+  B200MM_REQUIRE(a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, B200MM_ERR_ALIGN,
+                 "gemm: D must be 16B aligned with pitch %% 8 == 0 (ldd=%lld)", (long long)a->ldd);
+  B200MM_REQUIRE(!a->residual || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0), B200MM_ERR_ALIGN,
+                 "gemm: residual alignment");
+  B200MM_REQUIRE(!a->dact_in || (a->ld_dact % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dact_in) & 15) == 0), B200MM_ERR_ALIGN,
+                 "gemm: dact_in alignment");
+  B200MM_REQUIRE(!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, B200MM_ERR_ALIGN, "gemm: bias alignment");
+  B200MM_REQUIRE(!a->aux_out || (reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0, B200MM_ERR_ALIGN, "gemm: aux_out alignment");
+  B200MM_REQUIRE(a->act >= 0 && a->act <= 2, B200MM_ERR_SHAPE, "gemm: unknown activation %d", a->act);
+
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.m_tiles = static_cast<int32_t>(ceil_div(a->M, BM));
+  p.n_tiles = static_cast<int32_t>(ceil_div(a->N, BN));
+  p.kb_total = static_cast<int32_t>(ceil_div(a->K, BK));
+  int32_t splits = a->splits < 1 ? 1 : a->splits;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = static_cast<int32_t>(ceil_div(p.kb_total, splits));
+  splits = static_cast<int32_t>(ceil_div(p.kb_total, p.kb_per_split));  // no empty split
+  p.splits = splits;
+  p.partial = nullptr;
+  if (splits > 1) {
+    int64_t need = b200mm_gemm_workspace_bytes(a->M, a->N, splits);
+    B200MM_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, B200MM_ERR_SHAPE,
+                   "gemm: split-K needs %lld workspace bytes, got %lld", (long long)need, (long long)a->workspace_bytes);
+    B200MM_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, B200MM_ERR_ALIGN, "gemm: workspace alignment");
+    p.partial = reinterpret_cast<float*>(a->workspace);
+  }
+  p.mn_lbo = SLAB_BYTES; p.mn_sbo = 1024; p.k_lbo = 16; p.k_sbo = 1024;
+  if (const char* dbg = getenv("B200MM_DBG_DESC")) {  // bring-up only: "mn_lbo,mn_sbo,k_lbo,k_sbo" in bytes
+    unsigned v[4];
+    if (sscanf(dbg, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]) == 4) { p.mn_lbo = v[0]; p.mn_sbo = v[1]; p.k_lbo = v[2]; p.k_sbo = v[3]; }
+  }
+  p.epi.D = a->D; p.epi.ldd = a->ldd; p.epi.d_f32 = a->d_f32; p.epi.alpha = a->alpha;
+  p.epi.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
+  p.epi.act = a->act;
+  p.epi.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
+  p.epi.dact_in = reinterpret_cast<const __nv_bfloat16*>(a->dact_in);
+  p.epi.ld_dact = a->ld_dact;
+  p.epi.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.epi.ldr = a->ldr;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a->a_mn) rc = make_tmap_2d_bf16(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
+  else          rc = make_tmap_2d_bf16(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap_2d_bf16(&tmB, a->B, a->K, a->N, a->ldb, BK, BN);
+  else          rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
+  if (rc) return rc;
+
+  if (!a->a_mn && !a->b_mn) rc = launch_gemm<false, false>(tmA, tmB, p, stream);
+  else if (!a->a_mn && a->b_mn) rc = launch_gemm<false, true>(tmA, tmB, p, stream);
+  else if (a->a_mn && !a->b_mn) rc = launch_gemm<true, false>(tmA, tmB, p, stream);
+  else rc = launch_gemm<true, true>(tmA, tmB, p, stream);
+  if (rc) return rc;
+
+  if (splits > 1) {
+    const int64_t total = a->M * (a->N / 8);
+    int blocks = static_cast<int>(ceil_div(total, 256) < 148 * 8 ? ceil_div(total, 256) : 148 * 8);
+    gemm_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, a->M, a->N, splits, p.epi);
+    return check_launch("gemm_splitk_reduce_kernel");
+  }
+  return B200MM_OK;
+}

@@ -1,0 +1,127 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by running the UNMODIFIED reference (oracle/ref_loader.py).
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+The fixtures are small (tiny model configs) and committed, because the reference tree does not travel to the GPU box.
+
+Fixtures
+  cnclip_tiny.pt   reference CNCLIP (ViT 2L/64w/patch 8 @32px + BERT 2L/64h, embed 32), fp32, dropout 0:
+                   state_dict, inputs, forward outputs, symmetric-CE loss, gradients of every parameter
+  cnclip_tiny_h80.pt  same with vision_head_width=80-style odd head dim (width 160, 2 heads of 80) — ViT-H head geometry
+  losses.pt        get_mil_nce_loss / get_l1_simi_matrix / moco_loss known answers incl. SURVEY.md §8c (1)
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TINY = dict(
+    embed_dim=32,
+    image_resolution=32,
+    vision_layers=2,
+    vision_width=64,
+    vision_patch_size=8,
+    vocab_size=21128,  # FullTokenizer's [PAD]=0 lookup needs the bundled vocab; embeddings table sliced below
+    text_attention_probs_dropout_prob=0.0,
+    text_hidden_act="gelu",
+    text_hidden_dropout_prob=0.0,
+    text_hidden_size=64,
+    text_initializer_range=0.02,
+    text_intermediate_size=256,
+    text_max_position_embeddings=64,
+    text_num_attention_heads=2,
+    text_num_hidden_layers=2,
+    text_type_vocab_size=2,
+    vision_head_width=32,
+)
+
+
+def synth_text(B, L, vocab, gen):
+    """[CLS]=101 first, random ids, [SEP]=102 at the last valid position, [PAD]=0 after."""
+    ids = torch.randint(1, vocab, (B, L), generator=gen)
+    ids[:, 0] = 101
+    lens = torch.randint(4, L + 1, (B,), generator=gen)
+    for b in range(B):
+        ids[b, lens[b] - 1] = 102
+        ids[b, lens[b] :] = 0
+    return ids
+
+
+def make_cnclip(name, cfg, B, L, vocab_used):
+    cfg = dict(cfg)
+    cfg["vocab_size"] = vocab_used
+    model = ref_loader.build_cnclip(cfg, seed=0, dropout=0.0)
+    # give biases / LN params / logit-scale non-trivial values so that parity covers them
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("bias") or "LayerNorm.weight" in n or "ln_" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    model.train()
+    gen = torch.Generator().manual_seed(1234)
+    image = torch.randn(B, 3, cfg["image_resolution"], cfg["image_resolution"], generator=gen)
+    text = synth_text(B, L, vocab_used, gen)
+    img_f, txt_f, lpi, lpt = model(image, text)
+    labels = torch.arange(B)
+    loss = 0.5 * (F.cross_entropy(lpi, labels) + F.cross_entropy(lpt, labels))
+    loss.backward()
+    fx = {
+        "config": cfg,
+        "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "image": image,
+        "text": text,
+        "image_features": img_f.detach(),
+        "text_features": txt_f.detach(),
+        "logits_per_image": lpi.detach(),
+        "loss": loss.detach(),
+        "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None},
+    }
+    torch.save(fx, os.path.join(OUT, name))
+    print(name, "loss", float(loss.detach()), "params", sum(p.numel() for p in model.parameters()))
+
+
+def make_losses():
+    fn = ref_loader.load_loss_functions()
+    out = {}
+    # SURVEY.md §8c known answer (1)
+    torch.manual_seed(0)
+    B, D = 4, 8
+    t = F.normalize(torch.randn(B, D)).requires_grad_()
+    v = F.normalize(torch.randn(B, D)).requires_grad_()
+    sim = fn.get_l1_simi_matrix(None, t, v, 1, True).view(B, B)
+    loss = fn.get_mil_nce_loss(None, sim, B, 1)
+    loss.backward()
+    out["mil_b4"] = dict(t=t.detach(), v=v.detach(), loss=loss.detach(), dt=t.grad.clone(), dv=v.grad.clone())
+    # a larger, un-normalised case
+    torch.manual_seed(1)
+    B, D = 37, 24
+    t = (0.7 * torch.randn(B, D)).requires_grad_()
+    v = (0.7 * torch.randn(B, D)).requires_grad_()
+    sim = fn.get_l1_simi_matrix(None, t, v, 1, True).view(B, B)
+    loss = fn.get_mil_nce_loss(None, sim, B, 1)
+    loss.backward()
+    out["mil_b37"] = dict(t=t.detach(), v=v.detach(), loss=loss.detach(), dt=t.grad.clone(), dv=v.grad.clone())
+    # moco
+    import types
+
+    torch.manual_seed(2)
+    pos = torch.randn(9, 1)
+    neg = torch.randn(9, 50)
+    out["moco"] = dict(pos=pos, neg=neg, T=0.05, loss=fn.moco_loss(types.SimpleNamespace(T=0.05), pos, neg).detach())
+    torch.save(out, os.path.join(OUT, "losses.pt"))
+    print("losses.pt", {k: float(v["loss"]) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    make_cnclip("cnclip_tiny.pt", TINY, B=6, L=16, vocab_used=512)
+    h80 = dict(TINY, vision_width=160, vision_head_width=80, vision_layers=1, text_hidden_size=32,
+               text_num_attention_heads=2, text_num_hidden_layers=1, text_intermediate_size=64, embed_dim=16,
+               image_resolution=32, vision_patch_size=16)
+    make_cnclip("cnclip_tiny_h80.pt", h80, B=5, L=12, vocab_used=128)
+    make_losses()

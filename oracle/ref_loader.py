@@ -1,0 +1,127 @@
+"""TEST INFRASTRUCTURE — not product code.
+
+Loads the UNMODIFIED AntMMF reference modules of the hot path straight from the read-only reference tree
+(``/root/reference`` in the build container). ``import antmmf`` itself cannot work here (omegaconf, jsonlines,
+torchtext ... are not installed), so bare package objects are pre-seeded in ``sys.modules`` and only
+the plain-PyTorch files of the path are imported:
+
+  antmmf/modules/vision/backbone/clip/model.py          (VisionTransformer, ResidualAttentionBlock, LayerNorm, QuickGELU)
+  antmmf/modules/vision/backbone/clip/modeling_bert.py  (BertModel and its layers)
+  antmmf/modules/vision/backbone/clip/cn_model.py       (CNCLIP, CONFIGS)
+  antmmf/utils/distributed_utils.py                     (gather_tensor / GradientAllGather)
+
+The pure loss functions of ``prj/base_vtp/roi_univl/univl/model/univl_video_ret.py`` (module not importable) are
+extracted by AST and exec'd without modification (``get_mil_nce_loss`` :146-197, ``get_l1_simi_matrix`` :199-226,
+``reduce_clips`` :345-355) and likewise ``MocoUtils.moco_loss`` (``moco_utils.py:71-81``).
+
+Only ``tests/``, ``oracle/make_golden.py`` and ``bench.py --impl reference`` may import this module. The reference
+tree does not exist on the GPU box: callers must check :func:`available` first.
+"""
+import ast
+import contextlib
+import importlib
+import os
+import sys
+import textwrap
+import types
+
+REF_ROOT = os.environ.get("B200MM_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "antmmf/modules/vision/backbone/clip/cn_model.py"))
+
+
+_loaded = {}
+
+
+def _pkg(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    sys.modules[name] = m
+    return m
+
+
+def load():
+    """Returns a namespace with the reference modules: .model, .modeling_bert, .cn_model, .distributed_utils."""
+    if "ns" in _loaded:
+        return _loaded["ns"]
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+    R = REF_ROOT
+    if "antmmf" in sys.modules and not getattr(sys.modules["antmmf"], "_b200mm_stub", False):
+        raise RuntimeError("a real 'antmmf' package is already imported; the stub loader would shadow it")
+    a = _pkg("antmmf", R + "/antmmf")
+    a._b200mm_stub = True
+    c = _pkg("antmmf.common", R + "/antmmf/common")
+    c.configurable = lambda f=None, **kw: f if f is not None else (lambda g: g)
+    c.Configuration = type("Configuration", (dict,), {})
+    for p in ["modules", "modules/vision", "modules/vision/backbone", "modules/vision/backbone/clip", "utils"]:
+        _pkg("antmmf." + p.replace("/", "."), R + "/antmmf/" + p)
+    g = types.ModuleType("antmmf.utils.general")
+    g.nullcontext = contextlib.nullcontext
+    sys.modules["antmmf.utils.general"] = g
+    # modeling_bert.py:23-24 imports the flash-attn 1.x symbol whenever flash_attn is importable
+    fa = types.ModuleType("flash_attn.flash_attention")
+    fa.FlashMHA = None
+    sys.modules["flash_attn.flash_attention"] = fa
+    ns = types.SimpleNamespace()
+    ns.cn_model = importlib.import_module("antmmf.modules.vision.backbone.clip.cn_model")
+    ns.model = importlib.import_module("antmmf.modules.vision.backbone.clip.model")
+    ns.modeling_bert = importlib.import_module("antmmf.modules.vision.backbone.clip.modeling_bert")
+    ns.configuration_bert = importlib.import_module("antmmf.modules.vision.backbone.clip.configuration_bert")
+    ns.distributed_utils = importlib.import_module("antmmf.utils.distributed_utils")
+    _loaded["ns"] = ns
+    return ns
+
+
+def _extract_functions(relpath, names, extra_ns=None):
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    src = open(os.path.join(REF_ROOT, relpath)).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "np": np, "F": F, "get_package_version": lambda _: torch.__version__}
+    if extra_ns:
+        ns.update(extra_ns)
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            code = textwrap.dedent(ast.get_source_segment(src, node))
+            exec(compile(code, relpath, "exec"), ns)
+            found[node.name] = ns[node.name]
+    missing = set(names) - set(found)
+    if missing:
+        raise RuntimeError(f"functions {missing} not found in {relpath}")
+    return found
+
+
+def load_loss_functions():
+    """Reference loss arithmetic, unmodified, callable with ``self=None`` (or a namespace with ``.T`` for moco)."""
+    if "loss" in _loaded:
+        return _loaded["loss"]
+    ret = _extract_functions(
+        "prj/base_vtp/roi_univl/univl/model/univl_video_ret.py",
+        ["get_mil_nce_loss", "get_l1_simi_matrix", "reduce_clips"],
+    )
+    ret.update(_extract_functions("prj/base_vtp/roi_univl/univl/model/moco_utils.py", ["moco_loss"]))
+    ns = types.SimpleNamespace(**ret)
+    _loaded["loss"] = ns
+    return ns
+
+
+def build_cnclip(name_or_cfg, seed=0, dropout=0.0):
+    """Reference CNCLIP with the reference initialisation; ``text_projection`` (torch.empty in cn_model.py:190-192)
+    gets N(0, hidden^-0.5). Dropout probabilities are overridden (parity runs use 0)."""
+    import torch
+
+    ns = load()
+    cfg = dict(ns.cn_model.CONFIGS[name_or_cfg]) if isinstance(name_or_cfg, str) else dict(name_or_cfg)
+    cfg["text_attention_probs_dropout_prob"] = dropout
+    cfg["text_hidden_dropout_prob"] = dropout
+    torch.manual_seed(seed)
+    m = ns.cn_model.CNCLIP(**cfg)
+    with torch.no_grad():
+        m.text_projection.normal_(0.0, cfg["text_hidden_size"] ** -0.5)
+    return m

@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE — not product code.  CPU restatement (oracle) of the AntMMF ViT+BERT contrastive hot path.
+
+Plain PyTorch tensor arithmetic (fp32 by default, fp64 on request), written from the reference's algorithm and
+operating directly on a state-dict with the reference's parameter names. It exists so that parity can be checked on
+the GPU box, where ``/root/reference`` is absent; ``tests/test_oracle.py`` pins it (a) against the committed golden
+vectors under ``tests/golden/`` that were produced by the real reference (``oracle/make_golden.py``) and (b), when
+the reference tree is present, against the reference modules themselves.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg may import this file.
+The reference's own tests do not pin this path (it has no tests): parity is pinned by (a)/(b) only.
+
+Every function cites the reference code it restates (paths relative to the AntMMF tree).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------------------------------------------
+def layer_norm(x, w, b, eps):
+    """antmmf/modules/vision/backbone/clip/model.py:213-219 (fp32 compute) and modeling_bert.py:63 (nn.LayerNorm)."""
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def quick_gelu(x):
+    """clip/model.py:222-224."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def gelu_erf(x):
+    """clip/modeling_bert.py:31-37."""
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def mha(q, k, v, heads, key_bias=None):
+    """softmax(q k^T / sqrt(hd) + key_bias) v per head; q,k,v [B, L, W]; key_bias [B, L] additive or None.
+    ViT: nn.MultiheadAttention inside clip/model.py:231,245-251 (no mask); BERT: modeling_bert.py:144-165."""
+    B, L, W = q.shape
+    hd = W // heads
+    qh = q.view(B, L, heads, hd).transpose(1, 2)
+    kh = k.view(B, k.shape[1], heads, hd).transpose(1, 2)
+    vh = v.view(B, v.shape[1], heads, hd).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if key_bias is not None:
+        s = s + key_bias[:, None, None, :]
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B, L, W)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ViT  (clip/model.py:275-335; block :227-256)
+# ----------------------------------------------------------------------------------------------------------------
+def vit_block(sd, pfx, x, heads):
+    W = x.shape[-1]
+    h = layer_norm(x, sd[pfx + "ln_1.weight"], sd[pfx + "ln_1.bias"], 1e-5)
+    qkv = h @ sd[pfx + "attn.in_proj_weight"].t() + sd[pfx + "attn.in_proj_bias"]
+    a = mha(qkv[..., :W], qkv[..., W : 2 * W], qkv[..., 2 * W :], heads)
+    x = x + a @ sd[pfx + "attn.out_proj.weight"].t() + sd[pfx + "attn.out_proj.bias"]
+    h = layer_norm(x, sd[pfx + "ln_2.weight"], sd[pfx + "ln_2.bias"], 1e-5)
+    u = h @ sd[pfx + "mlp.c_fc.weight"].t() + sd[pfx + "mlp.c_fc.bias"]
+    x = x + quick_gelu(u) @ sd[pfx + "mlp.c_proj.weight"].t() + sd[pfx + "mlp.c_proj.bias"]
+    return x
+
+
+def patchify(image, p):
+    """[B,3,H,W] -> [B, (H/p)*(W/p), 3*p*p]; patch order row-major over the grid, feature order (c, dy, dx) — the
+    order in which nn.Conv2d(3, W, p, p).weight.view(W, -1) contracts (clip/model.py:289-295,310-312)."""
+    B, C, H, Wd = image.shape
+    g = H // p
+    x = image.view(B, C, g, p, Wd // p, p).permute(0, 2, 4, 1, 3, 5)
+    return x.reshape(B, g * (Wd // p), C * p * p)
+
+
+def vit_forward(sd, image, heads, pfx="", n_layers=None):
+    """VisionTransformer.forward, clip/model.py:309-335. Returns [B, E]."""
+    w = sd[pfx + "conv1.weight"]
+    width, p = w.shape[0], w.shape[-1]
+    x = patchify(image, p) @ w.reshape(width, -1).t()
+    cls = sd[pfx + "class_embedding"].expand(x.shape[0], 1, width)
+    x = torch.cat([cls, x], dim=1) + sd[pfx + "positional_embedding"]
+    x = layer_norm(x, sd[pfx + "ln_pre.weight"], sd[pfx + "ln_pre.bias"], 1e-5)
+    if n_layers is None:
+        n_layers = 1 + max(int(k[len(pfx) :].split(".")[2]) for k in sd if k.startswith(pfx + "transformer.resblocks."))
+    for i in range(n_layers):
+        x = vit_block(sd, f"{pfx}transformer.resblocks.{i}.", x, heads)
+    x = layer_norm(x[:, 0, :], sd[pfx + "ln_post.weight"], sd[pfx + "ln_post.bias"], 1e-5)
+    return x @ sd[pfx + "proj"]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BERT  (clip/modeling_bert.py)
+# ----------------------------------------------------------------------------------------------------------------
+def bert_embeddings(sd, pfx, input_ids, token_type_ids=None, eps=1e-12, inputs_embeds=None):
+    """BertEmbeddings.forward, modeling_bert.py:86-103 (inputs_embeds variant: prj/base_vtp/.../clip_text_encoder.py:36-60)."""
+    B, L = input_ids.shape if inputs_embeds is None else inputs_embeds.shape[:2]
+    we = sd[pfx + "word_embeddings.weight"][input_ids] if inputs_embeds is None else inputs_embeds
+    pe = sd[pfx + "position_embeddings.weight"][:L][None]
+    tt = torch.zeros(B, L, dtype=torch.long) if token_type_ids is None else token_type_ids
+    te = sd[pfx + "token_type_embeddings.weight"][tt]
+    return layer_norm(we + pe + te, sd[pfx + "LayerNorm.weight"], sd[pfx + "LayerNorm.bias"], eps)
+
+
+def bert_layer(sd, pfx, x, heads, key_bias, eps=1e-12):
+    """BertLayer.forward, modeling_bert.py:260-270 (post-LN)."""
+    q = x @ sd[pfx + "attention.self.query.weight"].t() + sd[pfx + "attention.self.query.bias"]
+    k = x @ sd[pfx + "attention.self.key.weight"].t() + sd[pfx + "attention.self.key.bias"]
+    v = x @ sd[pfx + "attention.self.value.weight"].t() + sd[pfx + "attention.self.value.bias"]
+    c = mha(q, k, v, heads, key_bias)
+    a = c @ sd[pfx + "attention.output.dense.weight"].t() + sd[pfx + "attention.output.dense.bias"]
+    x1 = layer_norm(a + x, sd[pfx + "attention.output.LayerNorm.weight"], sd[pfx + "attention.output.LayerNorm.bias"], eps)
+    i = gelu_erf(x1 @ sd[pfx + "intermediate.dense.weight"].t() + sd[pfx + "intermediate.dense.bias"])
+    o = i @ sd[pfx + "output.dense.weight"].t() + sd[pfx + "output.dense.bias"]
+    return layer_norm(o + x1, sd[pfx + "output.LayerNorm.weight"], sd[pfx + "output.LayerNorm.bias"], eps)
+
+
+def bert_encoder(sd, pfx, x, heads, attention_mask, eps=1e-12, n_layers=None):
+    """BertEncoder.forward (modeling_bert.py:283-314) with the additive mask of BertModel.forward (:487-497):
+    (1 - mask) * -10000 on the key axis."""
+    key_bias = (1.0 - attention_mask.to(x.dtype)) * -10000.0
+    if n_layers is None:
+        n_layers = 1 + max(int(k[len(pfx) :].split(".")[1]) for k in sd if k.startswith(pfx + "layer."))
+    for i in range(n_layers):
+        x = bert_layer(sd, f"{pfx}layer.{i}.", x, heads, key_bias, eps)
+    return x
+
+
+def bert_forward(sd, input_ids, attention_mask, heads, pfx="", eps=1e-12):
+    """BertModel.forward, modeling_bert.py:469-534. Returns sequence_output [B, L, H]."""
+    x = bert_embeddings(sd, pfx + "embeddings.", input_ids, eps=eps)
+    return bert_encoder(sd, pfx + "encoder.", x, heads, attention_mask, eps)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CN-CLIP dual encoder  (clip/cn_model.py:201-226)
+# ----------------------------------------------------------------------------------------------------------------
+def cnclip_forward(sd, image, text, vision_heads, text_heads, pad_id=0):
+    """CNCLIP.forward: returns (image_features, text_features, logits_per_image, logits_per_text)."""
+    img = vit_forward(sd, image, vision_heads, pfx="visual.")
+    mask = text.ne(pad_id)
+    seq = bert_forward(sd, text, mask, text_heads, pfx="bert.")
+    txt = seq[:, 0, :] @ sd["text_projection"]
+    img = img / img.norm(dim=-1, keepdim=True)
+    txt = txt / txt.norm(dim=-1, keepdim=True)
+    logits = sd["logit_scale"].exp() * img @ txt.t()
+    return img, txt, logits, logits.t()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------
+def symmetric_info_nce(logits_per_image):
+    """0.5*(CE(S, arange) + CE(S^T, arange)). The reference ships the one-direction form as CrossEn
+    (prj/dmae_vtp/roi_univl/univl/model/dmae_utils.py:528-537) applied both ways (univl_video_ret.py (dmae) :464-469)."""
+    S = logits_per_image
+    d = torch.diagonal(S)
+    return 0.5 * ((torch.logsumexp(S, 1) - d).mean() + (torch.logsumexp(S, 0) - d).mean())
+
+
+def mil_nce_n1(sim_t2v):
+    """UnivlForVideoTextRetrieval.get_mil_nce_loss (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197)
+    for n_clips == 1: sim_t2v[i, j] = text_i · video_j.
+    loss = mean_j( LSE( {S[i, j] for all i} ∪ {S[j, k] for k != j} ) - S[j, j] )."""
+    S = sim_t2v
+    B = S.shape[0]
+    eye = torch.eye(B, dtype=torch.bool)
+    row = S.masked_fill(eye, float("-inf"))  # text_j against all other videos
+    both = torch.cat([S.t(), row], dim=1)  # video_j against all texts, then the masked row
+    return (torch.logsumexp(both, dim=1) - torch.diagonal(S)).mean()
+
+
+def moco_nce(pos, neg, T):
+    """MocoUtils.moco_loss, prj/base_vtp/roi_univl/univl/model/moco_utils.py:71-81:
+    mean( LSE([pos, neg]/T) - LSE(pos/T) ); pos [N, P], neg [N, K]."""
+    allv = torch.cat([pos, neg], dim=1) / T
+    return (torch.logsumexp(allv, dim=1) - torch.logsumexp(pos / T, dim=1)).mean()
+
+
+def l1_simi_matrix(text, video, n_clips=1):
+    """get_l1_simi_matrix (univl_video_ret.py:199-226) with cal_cross=True: [B_t, B_v, n_clips]."""
+    E = text.shape[-1]
+    return torch.matmul(video.view(-1, n_clips, E), text.t()).permute(2, 0, 1)
+
+
+def to_dtype(sd, dtype):
+    return {k: (v.to(dtype) if torch.is_floating_point(v) else v) for k, v in sd.items()}

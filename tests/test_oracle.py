@@ -1,0 +1,94 @@
+"""Pins the CPU oracle (oracle/restated.py): against the committed golden vectors produced by the real reference
+(oracle/make_golden.py) and, when the reference tree is present, against the reference modules directly."""
+import os
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_loader, restated
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["cnclip_tiny.pt", "cnclip_tiny_h80.pt"])
+def test_restated_cnclip_matches_golden_forward_backward(golden_dir, name):
+    fx = _load(golden_dir, name)
+    cfg = fx["config"]
+    sd = {k: v.clone().requires_grad_(torch.is_floating_point(v)) for k, v in fx["state_dict"].items()}
+    vh = cfg["vision_width"] // cfg["vision_head_width"]
+    img, txt, lpi, lpt = restated.cnclip_forward(sd, fx["image"], fx["text"], vh, cfg["text_num_attention_heads"])
+    torch.testing.assert_close(img, fx["image_features"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(txt, fx["text_features"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(lpi, fx["logits_per_image"], rtol=1e-4, atol=1e-4)
+    loss = restated.symmetric_info_nce(lpi)
+    torch.testing.assert_close(loss, fx["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    for n, g in fx["grads"].items():
+        got = sd[n].grad
+        assert got is not None, n
+        denom = g.abs().max().clamp_min(1e-6)  # key.bias grads are analytically 0 (softmax shift invariance)
+        assert float((got - g).abs().max() / denom) < 2e-4, n
+
+
+def test_restated_losses_match_golden(golden_dir):
+    fx = _load(golden_dir, "losses.pt")
+    for key in ["mil_b4", "mil_b37"]:
+        c = fx[key]
+        t = c["t"].clone().requires_grad_()
+        v = c["v"].clone().requires_grad_()
+        sim = restated.l1_simi_matrix(t, v, 1).view(t.shape[0], v.shape[0])
+        loss = restated.mil_nce_n1(sim)
+        torch.testing.assert_close(loss, c["loss"], rtol=1e-5, atol=1e-6)
+        loss.backward()
+        torch.testing.assert_close(t.grad, c["dt"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(v.grad, c["dv"], rtol=1e-4, atol=1e-6)
+    # SURVEY.md §8c known answer (1)
+    assert abs(float(fx["mil_b4"]["loss"]) - 2.0541925) < 1e-6
+    assert abs(float(fx["mil_b4"]["dt"].abs().sum()) - 2.4046431) < 1e-5
+    assert abs(float(fx["mil_b4"]["dv"].abs().sum()) - 2.0970497) < 1e-5
+    m = fx["moco"]
+    torch.testing.assert_close(restated.moco_nce(m["pos"], m["neg"], m["T"]), m["loss"], rtol=1e-5, atol=1e-5)
+
+
+def test_patchify_equals_conv():
+    torch.manual_seed(0)
+    img = torch.randn(3, 3, 32, 48)
+    w = torch.randn(10, 3, 8, 8)
+    ref = F.conv2d(img, w, stride=8).flatten(2).transpose(1, 2)
+    got = restated.patchify(img, 8) @ w.reshape(10, -1).t()
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_restated_matches_live_reference():
+    ns = ref_loader.load()
+    cfg = dict(ns.cn_model.CONFIGS["ViT-B-16"])
+    cfg.update(vision_layers=1, text_num_hidden_layers=1, image_resolution=32, vocab_size=256,
+               text_hidden_dropout_prob=0.0, text_attention_probs_dropout_prob=0.0)
+    model = ref_loader.build_cnclip(cfg, seed=3)
+    torch.manual_seed(5)
+    image = torch.randn(3, 3, 32, 32)
+    text = torch.randint(1, 256, (3, 9))
+    text[:, 0] = 101
+    text[1, 5:] = 0
+    a = model(image, text)
+    sd = {k: v for k, v in model.state_dict().items()}
+    b = restated.cnclip_forward(sd, image, text, 12, 12)
+    for x, y in zip(a, b):
+        torch.testing.assert_close(y, x.detach(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_reference_loss_functions_extract():
+    fn = ref_loader.load_loss_functions()
+    torch.manual_seed(0)
+    t = F.normalize(torch.randn(4, 8))
+    v = F.normalize(torch.randn(4, 8))
+    sim = fn.get_l1_simi_matrix(None, t, v, 1, True).view(4, 4)
+    assert abs(float(fn.get_mil_nce_loss(None, sim, 4, 1)) - 2.0541925) < 1e-6
+    pos, neg = torch.randn(5, 1), torch.randn(5, 7)
+    torch.testing.assert_close(fn.moco_loss(types.SimpleNamespace(T=0.05), pos, neg), restated.moco_nce(pos, neg, 0.05))
