@@ -1,0 +1,125 @@
+"""All-pairs contrastive similarity + NCE losses on the b200mm kernels, sharded across ranks.
+
+Each rank owns B rows of both modalities. One all-gather brings every rank's normalised embeddings into contiguous
+[B_g, E] buffers (rank order = row order, like torch.cat in antmmf/utils/distributed_utils.py:185-188); the rank then
+computes only ITS rows of both logit blocks
+      A = s * I_loc · T_all^T     (image -> all texts)        Bt = s * T_loc · I_all^T   (text -> all images)
+with the tcgen05 GEMM whose epilogue reduces each 128x256 logit tile to (max, sum-exp) on the fly — the [B, B_g] logit
+matrices are never written. Backward recomputes the tiles, turns them into softmax gradients in the epilogue (bf16
+[B, B_g] per block — the only O(B·B_g) HBM object), and three more GEMMs produce the embedding gradients; gradients
+that belong to other ranks' rows go home through one reduce-scatter (= GradientAllGather.backward,
+distributed_utils.py:104-116).
+
+Loss scaling under data parallelism: a rank returns W * (its share of the global loss), so that the mean over ranks is
+the global loss and DDP's gradient averaging yields exactly the gradient of the global loss — the same result as the
+reference, where every rank evaluates the full B_g x B_g loss on gathered embeddings.
+"""
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _gather_rows(x, group, pad_to=8):
+    """[B, E] -> ([Bg_pad, E] all ranks' rows in rank order, zero rows appended up to a multiple of `pad_to`), Bg."""
+    rank, world = _world(group)
+    B, E = x.shape
+    Bg = B * world
+    Bg_pad = (Bg + pad_to - 1) // pad_to * pad_to
+    if world == 1 and Bg_pad == Bg:
+        return x, Bg
+    out = torch.zeros((Bg_pad, E), device=x.device, dtype=x.dtype)
+    if world == 1:
+        out[:B] = x
+    else:
+        dist.all_gather_into_tensor(out[:Bg], x.contiguous(), group=group)
+    return out, Bg
+
+
+def _scatter_grad(g_all, B, group):
+    """Sum over ranks of the gradient w.r.t. the gathered rows, returning this rank's [B, E] slice."""
+    rank, world = _world(group)
+    if world == 1:
+        return g_all[:B]
+    out = torch.empty((B, g_all.shape[1]), device=g_all.device, dtype=g_all.dtype)
+    dist.reduce_scatter_tensor(out, g_all[: B * world].contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+class _ContrastiveFn(Function):
+    """mode 'clip': 0.5*(CE(A, diag) + CE(Bt, diag)) / B_g     (cn_model.py:221-223 + CrossEn, dmae_utils.py:528-537)
+       mode 'mil' : mean_j( LSE(A[j,:] ∪ Bt[j, k != j]) - A[j,j] )  with a = video, b = text  (univl_video_ret.py:146-197, n_clips = 1)
+    a, b: [B, E] bf16 (already L2-normalised if the caller wants cosine similarity); log_scale: scalar tensor or None."""
+
+    @staticmethod
+    def forward(ctx, a, b, log_scale, mode, group):
+        rank, world = _world(group)
+        B, E = a.shape
+        alpha = float(torch.exp(log_scale.detach().float())) if log_scale is not None else 1.0
+        a_all, Bg = _gather_rows(a, group)
+        b_all, _ = _gather_rows(b, group)
+        off = rank * B
+        partsA = ops.contrast_lse_partials(a, b_all[:Bg], alpha, off)   # rows: a_loc, cols: all b
+        partsB = ops.contrast_lse_partials(b, a_all[:Bg], alpha, off)   # rows: b_loc, cols: all a
+        loss_sum = torch.zeros(1, device=a.device, dtype=torch.float32)
+        if mode == "clip":
+            lseA = ops.contrast_lse_merge(partsA[:2], None, partsA[2], False, loss_sum)
+            lseB = ops.contrast_lse_merge(partsB[:2], None, partsB[2], False, loss_sum)
+            denom = 2.0 * Bg
+        elif mode == "mil":
+            lseA = ops.contrast_lse_merge(partsA[:2], partsB[:2], partsA[2], True, loss_sum)
+            lseB = lseA
+            denom = float(Bg)
+        else:
+            raise ValueError(f"unknown contrastive mode {mode!r}")
+        ctx.save_for_backward(a, b, a_all, b_all, lseA, lseB)
+        ctx.meta = (mode, group, alpha, off, Bg, denom, world, log_scale.dtype if log_scale is not None else None)
+        # W * local share: mean over ranks == global loss (see module docstring)
+        return (loss_sum * (world / denom)).reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, a_all, b_all, lseA, lseB = ctx.saved_tensors
+        mode, group, alpha, off, Bg, denom, world, scale_dtype = ctx.meta
+        has_scale = scale_dtype is not None
+        B, E = a.shape
+        coef = float(gout) * world / denom
+        dscale = torch.zeros(1, device=a.device, dtype=torch.float32) if has_scale else None
+        # dL/dA and dL/dBt as bf16 [B, Bg_pad]; both blocks are softmax-minus-onehot of their row LSE
+        if mode == "clip":
+            GA = ops.contrast_softgrad(a, b_all, Bg, alpha, off, lseA, coef, 1.0, False, dscale)
+            GB = ops.contrast_softgrad(b, a_all, Bg, alpha, off, lseB, coef, 1.0, False, dscale)
+        else:
+            # union row: the positive appears once (in A); Bt's diagonal is excluded
+            GA = ops.contrast_softgrad(a, b_all, Bg, alpha, off, lseA, coef, 1.0, False, dscale)
+            GB = ops.contrast_softgrad(b, a_all, Bg, alpha, off, lseB, coef, 0.0, True, dscale)
+        # local-row gradients:  da = GA · b_all,  db = GB · a_all        (B operand read MN-major: [K = Bg_pad, N = E])
+        da = ops.gemm(GA, b_all, b_mn=True, out_f32=True)
+        db = ops.gemm(GB, a_all, b_mn=True, out_f32=True)
+        # gathered-row gradients: d b_all = GA^T · a,  d a_all = GB^T · b    (A operand MN-major: [K = B, M = Bg_pad])
+        db_all = ops.gemm(GA, a, a_mn=True, b_mn=True, out_f32=True)
+        da_all = ops.gemm(GB, b, a_mn=True, b_mn=True, out_f32=True)
+        da = da + _scatter_grad(da_all, B, group)
+        db = db + _scatter_grad(db_all, B, group)
+        d_ls = dscale.reshape(()).to(scale_dtype) if has_scale else None
+        return da.to(BF16), db.to(BF16), d_ls, None, None
+
+
+def clip_contrastive_loss(image_features, text_features, logit_scale, group=None):
+    """Symmetric InfoNCE over the global batch; features [B, E] bf16 (normalised), logit_scale = log-temperature parameter."""
+    d = _ContrastiveFn.apply(image_features, text_features, logit_scale, "clip", group)
+    return d
+
+
+def mil_nce_loss(video_features, text_features, group=None):
+    """UnivlForVideoTextRetrieval.get_mil_nce_loss for n_clips = 1 (no temperature)."""
+    return _ContrastiveFn.apply(video_features, text_features, None, "mil", group)

@@ -1,0 +1,241 @@
+// b200mm — small HBM-bound helpers around the GEMMs: activation recompute, bias / positional-embedding gradient
+// reductions, embedding scatter-add, L2 row normalisation, dtype casts, patch extraction (im2row).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace b200mm {
+
+__device__ __forceinline__ void unpack8e(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8e(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// y = act(x), n8 = number of 8-element vectors
+__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t n8, int act) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n8; i += gridDim.x * 256ll) {
+    float v[8];
+    unpack8e(x[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(act, v[j]);
+    y[i] = pack8e(v);
+  }
+}
+
+// out[(row % period), col] += in[row, col]   (fp32 atomics; caller zero-fills out)
+//   period == 1 : bias gradient   db[n] = sum_m dY[m, n]
+//   period == L : positional-embedding gradient  dpos[l, :] = sum_b ds[b*L + l, :]
+// block = 32 column groups (8 cols each) x 8 row lanes; grid = (col blocks, period, repeat chunks)
+__global__ void __launch_bounds__(256) rowsum_periodic_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                                              int64_t rows, int32_t W, int64_t period, int64_t reps_per_chunk) {
+  __shared__ float red[8][32 * 8 + 1];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cg) * 8;
+  const int64_t pidx = blockIdx.y;
+  const int64_t reps = rows / period;
+  const int64_t r0 = blockIdx.z * reps_per_chunk, r1 = min(reps, r0 + reps_per_chunk);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < W) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float v[8];
+      unpack8e(*reinterpret_cast<const uint4*>(in + (r * period + pidx) * W + col), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][c];
+  const int ocol = blockIdx.x * 256 + c;
+  if (ocol < W) atomicAdd(out + pidx * W + ocol, s);
+}
+
+// out[ids[row], :] += in[row, :] (fp32 atomics), rows with ids == skip_id are dropped (nn.Embedding padding_idx)
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ in, const int64_t* __restrict__ ids,
+                                                               float* __restrict__ out, int64_t rows, int32_t W, int64_t skip_id,
+                                                               int64_t n_out_rows) {
+  const int64_t w8 = W / 8;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < rows * w8; i += gridDim.x * 256ll) {
+    const int64_t row = i / w8;
+    const int col = static_cast<int>(i - row * w8) * 8;
+    const int64_t id = ids[row];
+    if (id == skip_id || id < 0 || id >= n_out_rows) continue;
+    float v[8];
+    unpack8e(*reinterpret_cast<const uint4*>(in + row * W + col), v);
+    float* o = out + id * W + col;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n,
+                                                            float scale) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) y[i] = __float2bfloat16(x[i] * scale);
+}
+
+// L2 row normalisation  y = x / ||x||   (cn_model.py:217-218, F.normalize in univl_video_base.py:114,158)
+// one warp per row; inv_norm saved for backward
+__global__ void __launch_bounds__(256) rownorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          float* __restrict__ inv_norm, int64_t rows, int32_t W, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float sq = 0.f;
+  for (int c = lane * 8; c < W; c += 256) {
+    float v[8];
+    unpack8e(*reinterpret_cast<const uint4*>(x + row * W + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+  }
+  sq = warp_sum(sq);
+  const float inv = 1.f / fmaxf(sqrtf(sq), eps);
+  if (lane == 0) inv_norm[row] = inv;
+  for (int c = lane * 8; c < W; c += 256) {
+    float v[8];
+    unpack8e(*reinterpret_cast<const uint4*>(x + row * W + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= inv;
+    *reinterpret_cast<uint4*>(y + row * W + c) = pack8e(v);
+  }
+}
+
+// dx = (dy - yhat * <yhat, dy>) * inv_norm, yhat = x * inv_norm recomputed in fp32 from x
+__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                          const float* __restrict__ inv_norm, __nv_bfloat16* __restrict__ dx,
+                                                          int64_t rows, int32_t W) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float inv = inv_norm[row];
+  float dot = 0.f;
+  for (int c = lane * 8; c < W; c += 256) {
+    float v[8];
+    unpack8e(*reinterpret_cast<const uint4*>(x + row * W + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot += v[j] * inv * dy[row * W + c + j];
+  }
+  dot = warp_sum(dot);
+  for (int c = lane * 8; c < W; c += 256) {
+    float v[8], o[8];
+    unpack8e(*reinterpret_cast<const uint4*>(x + row * W + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (dy[row * W + c + j] - v[j] * inv * dot) * inv;
+    *reinterpret_cast<uint4*>(dx + row * W + c) = pack8e(o);
+  }
+}
+
+// Patch extraction for the ViT stem (conv with stride == kernel == p, clip/model.py:289-295,310-312):
+//   out[b*(Np+1) + 1 + (gy*g + gx), (c*p + dy)*p + dx] = image[b, c, gy*p + dy, gx*p + dx]
+//   row b*(Np+1) + 0 (the class-token slot) and the K padding columns [3*p*p, Kp) are zero, so that the patch GEMM
+//   writes straight into the [B, Np+1, width] token buffer.
+__global__ void __launch_bounds__(256) im2row_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                                     int64_t B, int32_t C, int32_t H, int32_t Wd, int32_t p, int32_t Kp) {
+  const int g_y = H / p, g_x = Wd / p;
+  const int64_t L = static_cast<int64_t>(g_y) * g_x + 1;
+  const int64_t total = B * L * Kp;
+  const int K = C * p * p;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int k = static_cast<int>(i % Kp);
+    const int64_t row = i / Kp;
+    const int64_t b = row / L;
+    const int l = static_cast<int>(row - b * L);
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (l > 0 && k < K) {
+      const int pi = l - 1;
+      const int gy = pi / g_x, gx = pi - gy * g_x;
+      const int c = k / (p * p);
+      const int rem = k - c * p * p;
+      const int dy = rem / p, dx = rem - dy * p;
+      v = img[((b * C + c) * H + gy * p + dy) * Wd + gx * p + dx];
+    }
+    out[i] = v;
+  }
+}
+
+static inline int grid_for(int64_t work_items, int threads = 256, int waves = 8) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(work_items, threads), static_cast<int64_t>(sm_count()) * waves)));
+}
+
+}  // namespace b200mm
+
+using namespace b200mm;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream) {
+  B200MM_REQUIRE(n >= 0 && n % 8 == 0, B200MM_ERR_SHAPE, "act_fwd: n=%lld must be a multiple of 8", (long long)n);
+  if (n == 0) return B200MM_OK;
+  B200MM_REQUIRE(ALIGNED16(x) && ALIGNED16(y), B200MM_ERR_ALIGN, "act_fwd: pointers must be 16B aligned");
+  act_fwd_kernel<<<grid_for(n / 8), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n / 8, act);
+  return check_launch("act_fwd_kernel");
+}
+
+extern "C" int b200mm_rowsum_periodic(const void* in, float* out, int64_t rows, int32_t W, int64_t period, void* stream) {
+  B200MM_REQUIRE(rows >= 0 && W > 0 && W % 8 == 0 && period > 0 && rows % period == 0 && period <= 65535, B200MM_ERR_SHAPE,
+                 "rowsum_periodic: rows=%lld W=%d period=%lld", (long long)rows, W, (long long)period);
+  if (rows == 0) return B200MM_OK;
+  B200MM_REQUIRE(ALIGNED16(in), B200MM_ERR_ALIGN, "rowsum_periodic: input must be 16B aligned");
+  const int64_t reps = rows / period;
+  const int col_blocks = static_cast<int>(ceil_div(W, 256));
+  int64_t want_chunks = std::max<int64_t>(1, static_cast<int64_t>(sm_count()) * 4 / (col_blocks * period));
+  want_chunks = std::min<int64_t>(want_chunks, std::max<int64_t>(1, reps / 32));
+  want_chunks = std::min<int64_t>(want_chunks, 65535);
+  const int64_t per = ceil_div(reps, want_chunks);
+  dim3 grid(col_blocks, static_cast<unsigned>(period), static_cast<unsigned>(ceil_div(reps, per)));
+  rowsum_periodic_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, rows, W, period, per);
+  return check_launch("rowsum_periodic_kernel");
+}
+
+extern "C" int b200mm_scatter_add_rows(const void* in, const int64_t* ids, float* out, int64_t rows, int32_t W, int64_t skip_id,
+                                       int64_t n_out_rows, void* stream) {
+  B200MM_REQUIRE(rows >= 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "scatter_add_rows: rows=%lld W=%d", (long long)rows, W);
+  if (rows == 0) return B200MM_OK;
+  B200MM_REQUIRE(ALIGNED16(in), B200MM_ERR_ALIGN, "scatter_add_rows: input must be 16B aligned");
+  scatter_add_rows_kernel<<<grid_for(rows * (W / 8)), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), ids, out, rows,
+                                                                                  W, skip_id, n_out_rows);
+  return check_launch("scatter_add_rows_kernel");
+}
+
+extern "C" int b200mm_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* stream) {
+  if (n <= 0) return B200MM_OK;
+  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, scale);
+  return check_launch("cast_f32_bf16_kernel");
+}
+
+extern "C" int b200mm_rownorm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int32_t W, float eps, void* stream) {
+  B200MM_REQUIRE(rows >= 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "rownorm_fwd: rows=%lld W=%d", (long long)rows, W);
+  if (rows == 0) return B200MM_OK;
+  B200MM_REQUIRE(ALIGNED16(x) && ALIGNED16(y), B200MM_ERR_ALIGN, "rownorm_fwd: pointers must be 16B aligned");
+  rownorm_fwd_kernel<<<static_cast<int>(ceil_div(rows, 8)), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), inv_norm, rows, W, eps);
+  return check_launch("rownorm_fwd_kernel");
+}
+
+extern "C" int b200mm_rownorm_bwd(const float* dy, const void* x, const float* inv_norm, void* dx, int64_t rows, int32_t W, void* stream) {
+  B200MM_REQUIRE(rows >= 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "rownorm_bwd: rows=%lld W=%d", (long long)rows, W);
+  if (rows == 0) return B200MM_OK;
+  B200MM_REQUIRE(ALIGNED16(x) && ALIGNED16(dx), B200MM_ERR_ALIGN, "rownorm_bwd: pointers must be 16B aligned");
+  rownorm_bwd_kernel<<<static_cast<int>(ceil_div(rows, 8)), 256, 0, STREAM(stream)>>>(
+      dy, reinterpret_cast<const __nv_bfloat16*>(x), inv_norm, reinterpret_cast<__nv_bfloat16*>(dx), rows, W);
+  return check_launch("rownorm_bwd_kernel");
+}
+
+extern "C" int b200mm_im2row(const void* img, void* out, int64_t B, int32_t C, int32_t H, int32_t Wd, int32_t p, int32_t Kp, void* stream) {
+  B200MM_REQUIRE(B >= 0 && C > 0 && p > 0 && H % p == 0 && Wd % p == 0 && Kp >= C * p * p && Kp % 8 == 0, B200MM_ERR_SHAPE,
+                 "im2row: B=%lld C=%d H=%d W=%d p=%d Kp=%d", (long long)B, C, H, Wd, p, Kp);
+  if (B == 0) return B200MM_OK;
+  const int64_t L = static_cast<int64_t>(H / p) * (Wd / p) + 1;
+  im2row_kernel<<<grid_for(B * L * Kp), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(img),
+                                                                 reinterpret_cast<__nv_bfloat16*>(out), B, C, H, Wd, p, Kp);
+  return check_launch("im2row_kernel");
+}

@@ -45,12 +45,29 @@ struct EpiParams {
   int64_t ldr;
 };
 
+// epilogues of the contrastive-loss GEMMs (EPI_LSE / EPI_SOFTGRAD); z = alpha * <a_m, b_n> is the logit
+struct ContrastParams {
+  float* part_max;        // EPI_LSE: [M, n_tiles] running max of z over the tile's columns
+  float* part_sum;        // EPI_LSE: [M, n_tiles] sum exp(z - part_max)
+  float* diag;            // EPI_LSE: [M] z at column n == m + diag_off (the positive pair)
+  int64_t diag_off;
+  const float* row_lse;   // EPI_SOFTGRAD: [M] log-sum-exp each row is normalised with
+  float coef;             // EPI_SOFTGRAD: dL/dz = coef * (exp(z - row_lse[m]) - diag_sub * [n == m + diag_off])
+  float diag_sub;
+  int32_t diag_zero;      // EPI_SOFTGRAD: force dL/dz = 0 on the diagonal (MIL-NCE text->video block)
+  float* dscale;          // EPI_SOFTGRAD: += sum dL/dz * z  (gradient of the log-temperature), or null
+  int64_t n_valid;        // EPI_SOFTGRAD: columns >= n_valid are padding (G = 0 there)
+};
+
+enum { EPI_STD = 0, EPI_LSE = 1, EPI_SOFTGRAD = 2 };
+
 struct GemmParams {
   int64_t M, N, K;
   int32_t m_tiles, n_tiles, splits, kb_total, kb_per_split;
   float* partial;  // split-K: f32 [splits][M][N]; nullptr when splits == 1
   uint32_t mn_lbo, mn_sbo, k_lbo, k_sbo;  // descriptor byte offsets (defaults below; env-overridable for bring-up)
   EpiParams epi;
+  ContrastParams con;
 };
 
 // Full epilogue on 8 consecutive columns of one row (n % 8 == 0). Shared by the GEMM epilogue warps and the split-K
@@ -113,7 +130,7 @@ __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p)
   return c;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -230,28 +247,102 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if constexpr (EPI == EPI_STD) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (m < p.M) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (m < p.M) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int64_t n = n0 + c * 32 + g * 8;
-            if (n < p.N) {
-              float v[8];
+            for (int g = 0; g < 4; ++g) {
+              const int64_t n = n0 + c * 32 + g * 8;
+              if (n < p.N) {
+                float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              if (p.partial != nullptr) {
-                float* d = p.partial + (static_cast<int64_t>(tc.split) * p.M + m) * p.N + n;
-                *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                epi_apply8(v, m, n, p.epi);
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                if (p.partial != nullptr) {
+                  float* d = p.partial + (static_cast<int64_t>(tc.split) * p.M + m) * p.N + n;
+                  *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                  epi_apply8(v, m, n, p.epi);
+                }
               }
             }
           }
+        }
+      } else if constexpr (EPI == EPI_LSE) {
+        // online (max, sum-exp) over this tile's columns of row m; the diagonal logit is captured on the way
+        float mx = -INFINITY, sm = 0.f;
+        const int64_t dcol = m + p.con.diag_off;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int64_t nb = n0 + c * 32;
+          if (nb < p.N) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float z = nb + j < p.N ? __uint_as_float(r[j]) * p.epi.alpha : -INFINITY;
+              r[j] = __float_as_uint(z);
+              cm = fmaxf(cm, z);
+            }
+            const float nm = fmaxf(mx, cm);
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs += __expf(__uint_as_float(r[j]) - nm);
+            sm = sm * __expf(mx - nm) + cs;
+            mx = nm;
+            if (m < p.M && dcol >= nb && dcol < nb + 32 && dcol < p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j == dcol) p.con.diag[m] = __uint_as_float(r[j]);
+            }
+          }
+        }
+        if (m < p.M) {
+          p.con.part_max[m * p.n_tiles + tc.n_blk] = mx;
+          p.con.part_sum[m * p.n_tiles + tc.n_blk] = sm;
+        }
+      } else {
+        const float lse = m < p.M ? p.con.row_lse[m] : 0.f;
+        const int64_t dcol = m + p.con.diag_off;
+        float ds_acc = 0.f;
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.epi.D) + m * p.epi.ldd;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (m < p.M) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int64_t n = n0 + c * 32 + g * 8;
+              if (n < p.N) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float z = __uint_as_float(r[g * 8 + j]) * p.epi.alpha;
+                  const bool on_diag = (n + j == dcol);
+                  float gz = p.con.coef * (__expf(z - lse) - (on_diag ? p.con.diag_sub : 0.f));
+                  if ((on_diag && p.con.diag_zero) || n + j >= p.con.n_valid) gz = 0.f;
+                  ds_acc += gz * z;
+                  v[j] = gz * p.epi.alpha;  // dL/d<a_m, b_n>
+                }
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(drow + n) = o;
+              }
+            }
+          }
+        }
+        if (p.con.dscale != nullptr) {
+          ds_acc = warp_sum(ds_acc);
+          if (lane == 0) atomicAdd(p.con.dscale, ds_acc);
         }
       }
       tc_fence_before();
@@ -289,9 +380,9 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EPI = EPI_STD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI>;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
@@ -305,6 +396,34 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int grid = static_cast<int>(total_tiles < sm_count() ? total_tiles : sm_count());
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, p);
   return check_launch("gemm_tcgen05_kernel");
+}
+
+// Merge per-tile (max, sum-exp) partials of up to two logit blocks into one log-sum-exp per row.
+//   lse[m] = log( sum_t sumA[m,t] e^{maxA[m,t]} (+ sum_t sumB[m,t] e^{maxB[m,t]}) (- e^{diag[m]} if sub_diag) )
+//   loss_sum += sum_m (lse[m] - diag[m])            (fp32 atomic; caller zero-fills)
+// sub_diag implements MIL-NCE's union {video_j·all texts} ∪ {text_j·videos k != j}, where the positive logit would
+// otherwise be counted twice (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197).
+__global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ maxA, const float* __restrict__ sumA, int32_t tA,
+                                                        const float* __restrict__ maxB, const float* __restrict__ sumB, int32_t tB,
+                                                        const float* __restrict__ diag, int32_t sub_diag, float* __restrict__ lse,
+                                                        float* __restrict__ loss_sum, int64_t M) {
+  const int64_t m = blockIdx.x * 256ll + threadIdx.x;
+  float term = 0.f;
+  if (m < M) {
+    float mx = -INFINITY;
+    for (int t = 0; t < tA; ++t) mx = fmaxf(mx, maxA[m * tA + t]);
+    for (int t = 0; t < tB; ++t) mx = fmaxf(mx, maxB[m * tB + t]);
+    float sm = 0.f;
+    for (int t = 0; t < tA; ++t) sm += sumA[m * tA + t] * __expf(maxA[m * tA + t] - mx);
+    for (int t = 0; t < tB; ++t) sm += sumB[m * tB + t] * __expf(maxB[m * tB + t] - mx);
+    const float d = diag[m];
+    if (sub_diag) sm -= __expf(d - mx);
+    const float l = mx + __logf(sm);
+    lse[m] = l;
+    term = l - d;
+  }
+  term = warp_sum(term);
+  if ((threadIdx.x & 31) == 0 && loss_sum != nullptr) atomicAdd(loss_sum, term);
 }
 
 }  // namespace b200mm
@@ -387,4 +506,67 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
     return check_launch("gemm_splitk_reduce_kernel");
   }
   return B200MM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// contrastive similarity + log-softmax pieces (K8). Logits z[m,n] = alpha * <a_m, b_n> are produced tile by tile in
+// TMEM and consumed in the epilogue; the [M, N] logit matrix is never written to HBM in forward.
+// ---------------------------------------------------------------------------------------------------------------
+static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const void* a, int64_t lda, const void* b, int64_t ldb,
+                       int64_t M, int64_t N, int64_t K, float alpha) {
+  B200MM_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), B200MM_ERR_SHAPE,
+                 "contrast: M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  B200MM_REQUIRE(a && b, B200MM_ERR_SHAPE, "contrast: null operand");
+  p = GemmParams{};
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = static_cast<int32_t>(ceil_div(M, BM));
+  p.n_tiles = static_cast<int32_t>(ceil_div(N, BN));
+  p.kb_total = static_cast<int32_t>(ceil_div(K, BK));
+  p.kb_per_split = p.kb_total;
+  p.splits = 1;
+  p.partial = nullptr;
+  p.mn_lbo = SLAB_BYTES; p.mn_sbo = 1024; p.k_lbo = 16; p.k_sbo = 1024;
+  p.epi.alpha = alpha;
+  int rc = make_tmap_2d_bf16(&tmA, a, K, M, lda, BK, BM);
+  if (rc) return rc;
+  return make_tmap_2d_bf16(&tmB, b, K, N, ldb, BK, BN);
+}
+
+extern "C" int32_t b200mm_contrast_num_tiles(int64_t N) { return static_cast<int32_t>(ceil_div(N, BN)); }
+
+extern "C" int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                                            float alpha, int64_t diag_off, float* part_max, float* part_sum, float* diag,
+                                            void* stream) {
+  GemmParams p;
+  CUtensorMap tmA, tmB;
+  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, M, N, K, alpha);
+  if (rc) return rc;
+  B200MM_REQUIRE(part_max && part_sum && diag, B200MM_ERR_SHAPE, "contrast_lse_partials: null output");
+  p.con.part_max = part_max; p.con.part_sum = part_sum; p.con.diag = diag; p.con.diag_off = diag_off;
+  return launch_gemm<false, false, EPI_LSE>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mm_contrast_lse_merge(const float* maxA, const float* sumA, int32_t tilesA, const float* maxB, const float* sumB,
+                                         int32_t tilesB, const float* diag, int32_t sub_diag, float* lse, float* loss_sum, int64_t M,
+                                         void* stream) {
+  B200MM_REQUIRE(M > 0 && maxA && sumA && diag && lse && tilesA > 0 && (tilesB == 0 || (maxB && sumB)), B200MM_ERR_SHAPE,
+                 "contrast_lse_merge: bad arguments");
+  lse_merge_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      maxA, sumA, tilesA, maxB, sumB, tilesB, diag, sub_diag, lse, loss_sum, M);
+  return check_launch("lse_merge_kernel");
+}
+
+extern "C" int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                                        int64_t n_valid, float alpha, int64_t diag_off, const float* row_lse, float coef,
+                                        float diag_sub, int32_t diag_zero, void* G, int64_t ldg, float* dscale, void* stream) {
+  GemmParams p;
+  CUtensorMap tmA, tmB;
+  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, M, N, K, alpha);
+  if (rc) return rc;
+  B200MM_REQUIRE(row_lse && G && N % 8 == 0 && ldg % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, B200MM_ERR_ALIGN,
+                 "contrast_softgrad: G must be 16B aligned, N and ldg multiples of 8");
+  p.epi.D = G; p.epi.ldd = ldg;
+  p.con.row_lse = row_lse; p.con.coef = coef; p.con.diag_sub = diag_sub; p.con.diag_zero = diag_zero;
+  p.con.diag_off = diag_off; p.con.dscale = dscale; p.con.n_valid = n_valid;
+  return launch_gemm<false, false, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }

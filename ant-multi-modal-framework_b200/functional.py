@@ -1,0 +1,316 @@
+"""Block-level autograd glue: each Function runs a fixed sequence of b200mm kernels forward and backward.
+
+Block granularity (instead of per-op Functions) gives explicit control over what is kept for backward. Per ViT block
+the saved set is {x, qkv, o, lse, x_mid, u, LN statistics} = 10 T·W bf16 elements; LayerNorm outputs and the activated
+MLP hidden are recomputed in backward (HBM-bound, ~5 % of the block's GEMM time). With ``checkpoint=True`` only x is
+kept and the whole block forward is re-run in backward.
+
+Nothing here computes: all arithmetic is in the CUDA kernels behind b200mm.ops. torch supplies allocation, views,
+autograd bookkeeping and the occasional tiny copy (torch.cat of q/k/v weights, class-token row gather).
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import ACT_GELU_ERF, ACT_NONE, ACT_QUICKGELU  # noqa: F401
+
+BF16 = torch.bfloat16
+
+
+class _VecGrads:
+    """fp32 accumulators for the small per-block vector gradients (biases, LN affine) in ONE zero-filled buffer,
+    converted to bf16 views with a single cast kernel."""
+
+    def __init__(self, device, sizes):
+        self.sizes = sizes
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        self.buf = torch.zeros(self.offsets[-1], device=device, dtype=torch.float32)
+
+    def __getitem__(self, i):
+        return self.buf[self.offsets[i] : self.offsets[i + 1]]
+
+    def finish(self):
+        out = ops.cast_f32_bf16(self.buf)
+        return [out[self.offsets[i] : self.offsets[i + 1]] for i in range(len(self.sizes))]
+
+
+def _wgrad(dy, x):
+    """dW[out, in] = dY^T X with both operands read MN-major (no transposes through HBM)."""
+    return ops.gemm(dy, x, a_mn=True, b_mn=True)
+
+
+# ======================================================================================================================
+# ViT residual attention block (pre-LN) — antmmf/modules/vision/backbone/clip/model.py:227-256
+# ======================================================================================================================
+def _vit_block_forward(x, p, B, L, H, eps):
+    (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b) = p
+    W = x.shape[1]
+    h1, _, mean1, rstd1 = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
+    qkv = ops.gemm(h1, in_w, bias=in_b)
+    del h1
+    o, lse = ops.attention_fwd(qkv, B, L, H, W // H)
+    x_mid = ops.gemm(o, out_w, bias=out_b, residual=x)
+    h2, _, mean2, rstd2 = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+    g, u = ops.gemm(h2, fc_w, bias=fc_b, act=ACT_QUICKGELU, aux_out=True)
+    del h2
+    y = ops.gemm(g, proj_w, bias=proj_b, residual=x_mid)
+    return y, (mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u)
+
+
+class VitBlockFn(Function):
+    @staticmethod
+    def forward(ctx, x, ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b, B, L, H, eps, checkpoint):
+        p = (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b)
+        y, saved = _vit_block_forward(x, p, B, L, H, eps)
+        ctx.meta = (B, L, H, eps, checkpoint)
+        if checkpoint:
+            ctx.save_for_backward(x, *p)
+        else:
+            ctx.save_for_backward(x, *p, *saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, L, H, eps, checkpoint = ctx.meta
+        t = ctx.saved_tensors
+        x, p = t[0], t[1:13]
+        (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b) = p
+        if checkpoint:
+            _, saved = _vit_block_forward(x, p, B, L, H, eps)
+        else:
+            saved = t[13:]
+        mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u = saved
+        W = x.shape[1]
+        dy = dy.contiguous()
+        vg = _VecGrads(x.device, [W, W, 3 * W, W, W, W, 4 * W, W])  # ln1 w,b | in_b | out_b | ln2 w,b | fc_b | proj_b
+        # ---- MLP branch
+        g = ops.act_fwd(u, ACT_QUICKGELU)
+        d_proj_w = _wgrad(dy, g)
+        del g
+        ops.rowsum_periodic(dy, vg[7])
+        du = ops.gemm(dy, proj_w, b_mn=True, act=ACT_QUICKGELU, dact_in=u)
+        h2, _, _, _ = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+        d_fc_w = _wgrad(du, h2)
+        del h2
+        ops.rowsum_periodic(du, vg[6])
+        dh2 = ops.gemm(du, fc_w, b_mn=True)
+        del du
+        dx_mid = ops.layernorm_bwd(dh2, x_mid, mean2, rstd2, ln2_w, vg[4], vg[5], dadd=dy)
+        del dh2
+        # ---- attention branch
+        d_out_w = _wgrad(dx_mid, o)
+        ops.rowsum_periodic(dx_mid, vg[3])
+        d_o = ops.gemm(dx_mid, out_w, b_mn=True)
+        dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, L, H, W // H)
+        del d_o
+        h1, _, _, _ = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
+        d_in_w = _wgrad(dqkv, h1)
+        del h1
+        ops.rowsum_periodic(dqkv, vg[2])
+        dh1 = ops.gemm(dqkv, in_w, b_mn=True)
+        del dqkv
+        dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, vg[0], vg[1], dadd=dx_mid)
+        d_ln1_w, d_ln1_b, d_in_b, d_out_b, d_ln2_w, d_ln2_b, d_fc_b, d_proj_b = vg.finish()
+        return (dx, d_ln1_w, d_ln1_b, d_in_w, d_in_b, d_out_w, d_out_b, d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, d_proj_w, d_proj_b,
+                None, None, None, None, None)
+
+
+# ======================================================================================================================
+# ViT stem: conv1 patch embedding + class token + positional embedding + ln_pre — clip/model.py:309-324
+# ======================================================================================================================
+class VitStemFn(Function):
+    @staticmethod
+    def forward(ctx, image, conv_w, cls, pos, ln_w, ln_b, eps):
+        Bn, C, Hh, Ww = image.shape
+        width, _, p, _ = conv_w.shape
+        K = C * p * p
+        Kp = (K + 63) // 64 * 64
+        L = (Hh // p) * (Ww // p) + 1
+        if pos.shape[0] != L:
+            raise ops._lib.B200mmError(f"positional_embedding has {pos.shape[0]} rows, image gives {L} tokens")
+        patches = ops.im2row(image, p, Kp)
+        w2d = torch.zeros((width, Kp), device=image.device, dtype=BF16)
+        w2d[:, :K] = conv_w.reshape(width, K)
+        raw = ops.gemm(patches, w2d)
+        del patches
+        x0, s, mean, rstd = ops.layernorm_fwd(raw, ln_w, ln_b, eps, add0=pos, add1=cls, add_period=L, want_sum=True)
+        ctx.save_for_backward(image, s, mean, rstd, ln_w)
+        ctx.meta = (p, K, Kp, L, tuple(conv_w.shape))
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        image, s, mean, rstd, ln_w = ctx.saved_tensors
+        p, K, Kp, L, wshape = ctx.meta
+        W = s.shape[1]
+        vg = _VecGrads(s.device, [W, W, L * W])
+        ds = ops.layernorm_bwd(dx0.contiguous(), s, mean, rstd, ln_w, vg[0], vg[1])
+        ops.rowsum_periodic(ds, vg[2].view(L, W), period=L)
+        patches = ops.im2row(image, p, Kp)
+        d_w2d = _wgrad(ds, patches)  # class-token rows of `patches` are zero, so they drop out
+        d_conv = d_w2d[:, :K].reshape(wshape)
+        d_ln_w, d_ln_b, d_pos = vg.finish()
+        d_pos = d_pos.view(L, W)
+        return None, d_conv, d_pos[0].clone(), d_pos, d_ln_w, d_ln_b, None
+
+
+# ======================================================================================================================
+# Class-token head: ln_post(x[:, 0]) @ proj — clip/model.py:330-333;  text: seq[:, 0] @ text_projection — cn_model.py:210
+# ======================================================================================================================
+class ClsHeadFn(Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, proj, B, L, eps):
+        W = x.shape[1]
+        xc = x.view(B, L, W)[:, 0, :].contiguous()
+        if ln_w is not None:
+            h, _, mean, rstd = ops.layernorm_fwd(xc, ln_w, ln_b, eps)
+        else:
+            h, mean, rstd = xc, None, None
+        out = ops.gemm(h, proj, b_mn=True)  # proj is [W, E] = row-major [K, N]
+        ctx.meta = (B, L, ln_w is not None)
+        ctx.save_for_backward(xc, h, mean, rstd, ln_w, proj)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L, has_ln = ctx.meta
+        xc, h, mean, rstd, ln_w, proj = ctx.saved_tensors
+        W = xc.shape[1]
+        dout = dout.contiguous()
+        dh = ops.gemm(dout, proj)  # [B, W] = dout [B, E] · proj[W, E]^T
+        d_proj = ops.gemm(h, dout, a_mn=True, b_mn=True)  # [W, E] = h^T dout
+        d_ln_w = d_ln_b = None
+        if has_ln:
+            vg = _VecGrads(xc.device, [W, W])
+            dxc = ops.layernorm_bwd(dh, xc, mean, rstd, ln_w, vg[0], vg[1])
+            d_ln_w, d_ln_b = vg.finish()
+        else:
+            dxc = dh
+        dx = torch.zeros((B * L, W), device=xc.device, dtype=BF16)
+        dx.view(B, L, W)[:, 0, :] = dxc
+        return dx, d_ln_w, d_ln_b, d_proj, None, None, None
+
+
+# ======================================================================================================================
+# BERT layer (post-LN) — antmmf/modules/vision/backbone/clip/modeling_bert.py:253-270
+# ======================================================================================================================
+def _bert_layer_forward(x, p, key_bias, B, L, H, eps):
+    (qkv_w, qkv_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b) = p
+    Hd = x.shape[1]
+    qkv = ops.gemm(x, qkv_w, bias=qkv_b)
+    c, lse = ops.attention_fwd(qkv, B, L, H, Hd // H, key_bias=key_bias)
+    s1 = ops.gemm(c, o_w, bias=o_b, residual=x)
+    x1, _, mean1, rstd1 = ops.layernorm_fwd(s1, ln1_w, ln1_b, eps)
+    g, u = ops.gemm(x1, i_w, bias=i_b, act=ACT_GELU_ERF, aux_out=True)
+    s2 = ops.gemm(g, d_w, bias=d_b, residual=x1)
+    del g, x1
+    y, _, mean2, rstd2 = ops.layernorm_fwd(s2, ln2_w, ln2_b, eps)
+    return y, (qkv, c, lse, s1, mean1, rstd1, u, s2, mean2, rstd2)
+
+
+class BertLayerFn(Function):
+    @staticmethod
+    def forward(ctx, x, q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b, key_bias, B, L, H,
+                eps, checkpoint):
+        qkv_w = torch.cat([q_w, k_w, v_w], dim=0)
+        qkv_b = torch.cat([q_b, k_b, v_b], dim=0)
+        p = (qkv_w, qkv_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b)
+        y, saved = _bert_layer_forward(x, p, key_bias, B, L, H, eps)
+        ctx.meta = (B, L, H, eps, checkpoint, key_bias is not None)
+        kb = (key_bias,) if key_bias is not None else ()
+        if checkpoint:
+            ctx.save_for_backward(x, *p, *kb)
+        else:
+            ctx.save_for_backward(x, *p, *kb, *saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, L, H, eps, checkpoint, has_kb = ctx.meta
+        t = ctx.saved_tensors
+        x, p = t[0], t[1:13]
+        key_bias = t[13] if has_kb else None
+        rest = t[13 + int(has_kb) :]
+        (qkv_w, qkv_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b) = p
+        if checkpoint:
+            _, rest = _bert_layer_forward(x, p, key_bias, B, L, H, eps)
+        qkv, c, lse, s1, mean1, rstd1, u, s2, mean2, rstd2 = rest
+        Hd = x.shape[1]
+        I = i_w.shape[0]
+        vg = _VecGrads(x.device, [3 * Hd, Hd, Hd, Hd, I, Hd, Hd, Hd])  # qkv_b | o_b | ln1 w,b | i_b | d_b | ln2 w,b
+        ds2 = ops.layernorm_bwd(dy.contiguous(), s2, mean2, rstd2, ln2_w, vg[6], vg[7])
+        g = ops.act_fwd(u, ACT_GELU_ERF)
+        d_d_w = _wgrad(ds2, g)
+        del g
+        ops.rowsum_periodic(ds2, vg[5])
+        du = ops.gemm(ds2, d_w, b_mn=True, act=ACT_GELU_ERF, dact_in=u)
+        x1, _, _, _ = ops.layernorm_fwd(s1, ln1_w, ln1_b, eps)
+        d_i_w = _wgrad(du, x1)
+        del x1
+        ops.rowsum_periodic(du, vg[4])
+        dx1 = ops.gemm(du, i_w, b_mn=True, residual=ds2)  # + ds2: x1 also feeds the output residual
+        del du, ds2
+        ds1 = ops.layernorm_bwd(dx1, s1, mean1, rstd1, ln1_w, vg[2], vg[3])
+        del dx1
+        d_o_w = _wgrad(ds1, c)
+        ops.rowsum_periodic(ds1, vg[1])
+        dc = ops.gemm(ds1, o_w, b_mn=True)
+        dqkv = ops.attention_bwd(qkv, c, dc, lse, B, L, H, Hd // H, key_bias=key_bias)
+        del dc
+        d_qkv_w = _wgrad(dqkv, x)
+        ops.rowsum_periodic(dqkv, vg[0])
+        dx = ops.gemm(dqkv, qkv_w, b_mn=True, residual=ds1)  # + ds1: x also feeds the attention residual
+        d_qkv_b, d_o_b, d_ln1_w, d_ln1_b, d_i_b, d_d_b, d_ln2_w, d_ln2_b = vg.finish()
+        dq_w, dk_w, dv_w = d_qkv_w[:Hd], d_qkv_w[Hd : 2 * Hd], d_qkv_w[2 * Hd :]
+        dq_b, dk_b, dv_b = d_qkv_b[:Hd], d_qkv_b[Hd : 2 * Hd], d_qkv_b[2 * Hd :]
+        return (dx, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_o_w, d_o_b, d_ln1_w, d_ln1_b, d_i_w, d_i_b, d_d_w, d_d_b, d_ln2_w, d_ln2_b,
+                None, None, None, None, None, None)
+
+
+# ======================================================================================================================
+# BERT embeddings — modeling_bert.py:66-103 (inputs_embeds variant: prj/base_vtp/.../clip_text_encoder.py:36-60)
+# ======================================================================================================================
+class BertEmbeddingsFn(Function):
+    @staticmethod
+    def forward(ctx, word_or_embeds, ids, pos_table, type_table, type_ids, ln_w, ln_b, L, eps, padding_idx, from_embeds):
+        # from_embeds: word_or_embeds is [rows, H] (already embedded tokens), ids = arange(rows)
+        y, s, mean, rstd = ops.embed_layernorm_fwd(word_or_embeds, ids, pos_table, L, type_table, type_ids, ln_w, ln_b, eps)
+        ctx.save_for_backward(s, mean, rstd, ln_w, ids, type_ids)
+        ctx.meta = (L, padding_idx, from_embeds, word_or_embeds.shape[0], pos_table.shape[0], type_table.shape[0])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, mean, rstd, ln_w, ids, type_ids = ctx.saved_tensors
+        L, padding_idx, from_embeds, n_word, n_pos, n_type = ctx.meta
+        Hd = s.shape[1]
+        vg = _VecGrads(s.device, [Hd, Hd, n_pos * Hd, n_type * Hd])
+        ds = ops.layernorm_bwd(dy.contiguous(), s, mean, rstd, ln_w, vg[0], vg[1])
+        ops.rowsum_periodic(ds, vg[2].view(n_pos, Hd)[:L], period=L)
+        ops.scatter_add_rows(ds, type_ids, vg[3].view(n_type, Hd))
+        if from_embeds:
+            d_word = ds
+        else:
+            acc = torch.zeros((n_word, Hd), device=s.device, dtype=torch.float32)
+            ops.scatter_add_rows(ds, ids, acc, skip_id=padding_idx if padding_idx is not None else -1)
+            d_word = ops.cast_f32_bf16(acc)
+        d_ln_w, d_ln_b, d_pos, d_type = vg.finish()
+        return d_word, None, d_pos.view(n_pos, Hd), d_type.view(n_type, Hd), None, d_ln_w, d_ln_b, None, None, None, None
+
+
+# ======================================================================================================================
+# L2 row normalisation — cn_model.py:217-218
+# ======================================================================================================================
+class RowNormFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y, inv = ops.rownorm_fwd(x)
+        ctx.save_for_backward(x, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, inv = ctx.saved_tensors
+        return ops.rownorm_bwd(dy.float().contiguous(), x, inv)

@@ -1,0 +1,332 @@
+"""Tensor-level wrappers of the C-ABI (one Python function per kernel entry point; no arithmetic happens here).
+
+torch is used for allocation, stream handles and dtype/shape checks only. Every function requires CUDA tensors and
+raises otherwise: the product path has no CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_QUICKGELU  # noqa: F401
+
+BF16 = torch.bfloat16
+
+# bookkeeping for bench.py: number of b200mm kernels launched, and (when enabled) CUDA-event timing of every GEMM launch
+LAUNCHES = 0
+GEMM_PROFILE = None  # set to a list to collect (flops, start_event, stop_event) per tcgen05 GEMM launch
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, name, dtype=BF16, dim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B200mmError(f"b200mm: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.B200mmError(f"b200mm: `{name}` must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise _lib.B200mmError(f"b200mm: `{name}` must be {dim}-D, got shape {tuple(t.shape)}")
+    return t
+
+
+def _row_major_2d(t, name):
+    _req(t, name, BF16, 2)
+    if t.stride(1) != 1:
+        raise _lib.B200mmError(f"b200mm: `{name}` must have unit inner stride, got strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+_SM = {}
+
+
+def sm_count():
+    d = torch.cuda.current_device()
+    if d not in _SM:
+        _SM[d] = torch.cuda.get_device_properties(d).multi_processor_count
+    return _SM[d]
+
+
+def pick_splits(M, N, K, max_splits=32):
+    """Split-K factor for GEMMs with few output tiles (weight gradients): maximise wave efficiency over the SMs."""
+    tiles = math.ceil(M / 128) * math.ceil(N / 256)
+    kb = math.ceil(K / 64)
+    sms = sm_count()
+    if tiles >= sms or kb < 16:
+        return 1
+    best, best_eff = 1, 0.0
+    for s in range(1, max_splits + 1):
+        if kb // s < 8:
+            break
+        ctas = tiles * s
+        eff = ctas / (math.ceil(ctas / sms) * sms)
+        if eff > best_eff + 0.03:
+            best, best_eff = s, eff
+    return best
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False, dact_in=None, residual=None, alpha=1.0,
+         out=None, out_f32=False, splits=None):
+    """D = epilogue(alpha * A·B^T) on the tcgen05 GEMM (b200mm_gemm_bf16).
+
+    a: [M, K] (a_mn=False) or [K, M] (a_mn=True, reduction index slow);  b: [N, K] (b_mn=False) or [K, N] (b_mn=True).
+    Returns D [M, N] (bf16, or f32 if out_f32) — and the pre-activation copy if aux_out.
+    """
+    lib = _lib.load()
+    lda = _row_major_2d(a, "a")
+    ldb = _row_major_2d(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise _lib.B200mmError(f"b200mm.gemm: reduction dims differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else BF16)
+    else:
+        _req(out, "out", torch.float32 if out_f32 else BF16, 2)
+    aux = torch.empty((M, N), device=a.device, dtype=BF16) if aux_out else None
+    if splits is None:
+        splits = pick_splits(M, N, K)
+    ws = None
+    ws_bytes = 0
+    if splits > 1:
+        ws_bytes = lib.b200mm_gemm_workspace_bytes(M, N, splits)
+        ws = torch.empty(ws_bytes // 4, device=a.device, dtype=torch.float32)
+    g = _lib.GemmArgs()
+    g.A, g.lda, g.a_mn = a.data_ptr(), lda, int(a_mn)
+    g.B, g.ldb, g.b_mn = b.data_ptr(), ldb, int(b_mn)
+    g.D, g.ldd, g.d_f32 = out.data_ptr(), out.stride(0), int(out_f32)
+    g.M, g.N, g.K = M, N, K
+    g.alpha = alpha
+    g.bias = _req(bias, "bias", BF16, 1).data_ptr() if bias is not None else None
+    g.act = act
+    g.aux_out = aux.data_ptr() if aux is not None else None
+    if dact_in is not None:
+        g.dact_in, g.ld_dact = dact_in.data_ptr(), _row_major_2d(dact_in, "dact_in")
+    if residual is not None:
+        g.residual, g.ldr = residual.data_ptr(), _row_major_2d(residual, "residual")
+    g.splits = splits
+    g.workspace = ws.data_ptr() if ws is not None else None
+    g.workspace_bytes = ws_bytes
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib.b200mm_gemm_bf16(ctypes.byref(g), _stream()), "b200mm_gemm_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append((2.0 * M * N * K, e0, e1, splits))
+    _count(2 if splits > 1 else 1)
+    return (out, aux) if aux_out else out
+
+
+def layernorm_fwd(x, w, b, eps, add0=None, add1=None, add_period=0, want_sum=False):
+    """y = LN(x + add0[row % period] + add1·[row % period == 0]); returns (y, s_or_None, mean, rstd)."""
+    lib = _lib.load()
+    _req(x, "x", BF16, 2)
+    rows, W = x.shape
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if want_sum else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(
+        lib.b200mm_layernorm_fwd(_ptr(x), _ptr(add0), _ptr(add1), add_period, _ptr(_req(w, "w", BF16, 1)), _ptr(_req(b, "b", BF16, 1)),
+                                 _ptr(y), _ptr(s), _ptr(mean), _ptr(rstd), rows, W, eps, _stream()),
+        "b200mm_layernorm_fwd")
+    _count(1)
+    return y, s, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, w, dw32, db32, dadd=None):
+    """dx = LN'(dy) (+ dadd); dw32/db32 (f32 [W]) are accumulated into."""
+    lib = _lib.load()
+    _req(dy, "dy", BF16, 2)
+    rows, W = dy.shape
+    dx = torch.empty_like(dy)
+    _lib.check(
+        lib.b200mm_layernorm_bwd(_ptr(dy), _ptr(_req(x, "x", BF16, 2)), _ptr(mean), _ptr(rstd), _ptr(w), _ptr(dadd), _ptr(dx),
+                                 _ptr(_req(dw32, "dw", torch.float32)), _ptr(_req(db32, "db", torch.float32)), rows, W, _stream()),
+        "b200mm_layernorm_bwd")
+    _count(1)
+    return dx
+
+
+def embed_layernorm_fwd(word, ids, pos, L, type_table, type_ids, w, b, eps):
+    lib = _lib.load()
+    _req(word, "word", BF16, 2)
+    _req(ids, "ids", torch.int64)
+    _req(type_ids, "type_ids", torch.int64)
+    rows, W = ids.numel(), word.shape[1]
+    y = torch.empty((rows, W), device=word.device, dtype=BF16)
+    s = torch.empty_like(y)
+    mean = torch.empty(rows, device=word.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    _lib.check(
+        lib.b200mm_embed_layernorm_fwd(_ptr(word), _ptr(ids), _ptr(_req(pos, "pos", BF16, 2)), L, _ptr(_req(type_table, "type", BF16, 2)),
+                                       _ptr(type_ids), _ptr(w), _ptr(b), _ptr(y), _ptr(s), _ptr(mean), _ptr(rstd), rows, W, eps, _stream()),
+        "b200mm_embed_layernorm_fwd")
+    _count(1)
+    return y, s, mean, rstd
+
+
+def attention_fwd(qkv, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=None):
+    """qkv: [B*L, ld] fused projection; returns (o [B*L, H*hd], lse [B, H, L])."""
+    lib = _lib.load()
+    ld = _row_major_2d(qkv, "qkv")
+    W = H * hd
+    k_off = W if k_off is None else k_off
+    v_off = 2 * W if v_off is None else v_off
+    o = torch.empty((B * L, W), device=qkv.device, dtype=BF16)
+    lse = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
+    if key_bias is not None:
+        _req(key_bias, "key_bias", torch.float32, 2)
+    _lib.check(
+        lib.b200mm_attention_fwd(_ptr(qkv), ld, q_off, k_off, v_off, _ptr(o), W, _ptr(lse), _ptr(key_bias), B, H, L, hd,
+                                 1.0 / math.sqrt(hd), _stream()),
+        "b200mm_attention_fwd")
+    _count(1)
+    return o, lse
+
+
+def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=None):
+    lib = _lib.load()
+    ld = _row_major_2d(qkv, "qkv")
+    W = H * hd
+    k_off = W if k_off is None else k_off
+    v_off = 2 * W if v_off is None else v_off
+    _req(d_o, "d_o", BF16, 2)
+    if not d_o.is_contiguous():
+        raise _lib.B200mmError("b200mm.attention_bwd: d_o must be contiguous")
+    dqkv = torch.empty_like(qkv)
+    dsum = torch.empty_like(lse)
+    _lib.check(
+        lib.b200mm_attention_bwd(_ptr(qkv), ld, q_off, k_off, v_off, _ptr(o), _ptr(d_o), W, _ptr(lse), _ptr(key_bias), _ptr(dqkv),
+                                 _ptr(dsum), B, H, L, hd, 1.0 / math.sqrt(hd), _stream()),
+        "b200mm_attention_bwd")
+    _count(2)
+    return dqkv
+
+
+def act_fwd(x, act):
+    lib = _lib.load()
+    _req(x, "x", BF16)
+    y = torch.empty_like(x)
+    _lib.check(lib.b200mm_act_fwd(_ptr(x), _ptr(y), x.numel(), act, _stream()), "b200mm_act_fwd")
+    _count(1)
+    return y
+
+
+def rowsum_periodic(x, out32, period=1):
+    """out32[(row % period), :] += x[row, :]"""
+    lib = _lib.load()
+    _req(x, "x", BF16, 2)
+    _req(out32, "out", torch.float32)
+    _lib.check(lib.b200mm_rowsum_periodic(_ptr(x), _ptr(out32), x.shape[0], x.shape[1], period, _stream()), "b200mm_rowsum_periodic")
+    _count(1)
+
+
+def scatter_add_rows(x, ids, out32, skip_id=-1):
+    lib = _lib.load()
+    _req(x, "x", BF16, 2)
+    _req(ids, "ids", torch.int64)
+    _req(out32, "out", torch.float32, 2)
+    _lib.check(lib.b200mm_scatter_add_rows(_ptr(x), _ptr(ids), _ptr(out32), x.shape[0], x.shape[1], skip_id, out32.shape[0], _stream()),
+               "b200mm_scatter_add_rows")
+    _count(1)
+
+
+def cast_f32_bf16(x32, scale=1.0):
+    lib = _lib.load()
+    _req(x32, "x", torch.float32)
+    y = torch.empty(x32.shape, device=x32.device, dtype=BF16)
+    _lib.check(lib.b200mm_cast_f32_bf16(_ptr(x32), _ptr(y), x32.numel(), scale, _stream()), "b200mm_cast_f32_bf16")
+    _count(1)
+    return y
+
+
+def rownorm_fwd(x, eps=1e-12):
+    lib = _lib.load()
+    _req(x, "x", BF16, 2)
+    y = torch.empty_like(x)
+    inv = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_rownorm_fwd(_ptr(x), _ptr(y), _ptr(inv), x.shape[0], x.shape[1], eps, _stream()), "b200mm_rownorm_fwd")
+    _count(1)
+    return y, inv
+
+
+def rownorm_bwd(dy32, x, inv):
+    lib = _lib.load()
+    _req(dy32, "dy", torch.float32, 2)
+    dx = torch.empty_like(x)
+    _lib.check(lib.b200mm_rownorm_bwd(_ptr(dy32), _ptr(x), _ptr(inv), _ptr(dx), x.shape[0], x.shape[1], _stream()), "b200mm_rownorm_bwd")
+    _count(1)
+    return dx
+
+
+def im2row(img, p, Kp):
+    """[B, C, H, W] bf16 -> [B*(Np+1), Kp] patch matrix with a zero row per image for the class token."""
+    lib = _lib.load()
+    _req(img, "img", BF16, 4)
+    if not img.is_contiguous():
+        raise _lib.B200mmError("b200mm.im2row: image must be contiguous NCHW")
+    B, C, H, W = img.shape
+    L = (H // p) * (W // p) + 1
+    out = torch.empty((B * L, Kp), device=img.device, dtype=BF16)
+    _lib.check(lib.b200mm_im2row(_ptr(img), _ptr(out), B, C, H, W, p, Kp, _stream()), "b200mm_im2row")
+    _count(1)
+    return out
+
+
+def contrast_lse_partials(a, b, alpha, diag_off):
+    """Per-row (max, sum-exp) partials of z = alpha * a·b^T over 256-column tiles + the diagonal logit."""
+    lib = _lib.load()
+    lda = _row_major_2d(a, "a")
+    ldb = _row_major_2d(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    nt = lib.b200mm_contrast_num_tiles(N)
+    pmax = torch.empty((M, nt), device=a.device, dtype=torch.float32)
+    psum = torch.empty_like(pmax)
+    diag = torch.zeros(M, device=a.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_contrast_lse_partials(_ptr(a), lda, _ptr(b), ldb, M, N, K, alpha, diag_off, _ptr(pmax), _ptr(psum), _ptr(diag),
+                                                _stream()), "b200mm_contrast_lse_partials")
+    _count(1)
+    return pmax, psum, diag
+
+
+def contrast_lse_merge(partsA, partsB, diag, sub_diag, loss_sum):
+    lib = _lib.load()
+    maxA, sumA = partsA
+    M = maxA.shape[0]
+    lse = torch.empty(M, device=maxA.device, dtype=torch.float32)
+    maxB, sumB = partsB if partsB is not None else (None, None)
+    _lib.check(lib.b200mm_contrast_lse_merge(_ptr(maxA), _ptr(sumA), maxA.shape[1], _ptr(maxB), _ptr(sumB),
+                                             maxB.shape[1] if maxB is not None else 0, _ptr(diag), int(sub_diag), _ptr(lse),
+                                             _ptr(loss_sum), M, _stream()), "b200mm_contrast_lse_merge")
+    _count(1)
+    return lse
+
+
+def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, diag_zero, dscale):
+    """G = alpha*coef*(exp(z - row_lse) - diag_sub*[diag]) as bf16 [M, N]; dscale (f32 scalar tensor or None) += sum dL/dz * z.
+    b may carry zero padding rows up to a multiple of 8; columns >= n_valid are zeroed."""
+    lib = _lib.load()
+    lda = _row_major_2d(a, "a")
+    ldb = _row_major_2d(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    G = torch.empty((M, N), device=a.device, dtype=BF16)
+    _lib.check(lib.b200mm_contrast_softgrad(_ptr(a), lda, _ptr(b), ldb, M, N, K, n_valid, alpha, diag_off, _ptr(row_lse), coef, diag_sub,
+                                            int(diag_zero), _ptr(G), N, _ptr(dscale), _stream()), "b200mm_contrast_softgrad")
+    _count(1)
+    return G

@@ -1,0 +1,328 @@
+"""bench.py — image-text pairs/s, forward+backward, of the ViT+BERT contrastive hot path (BASELINE.json `metric`).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference algorithm on the host CPU cores)
+
+A "step" = one fused forward + contrastive loss + backward over one synthetic batch (optimizer step and data loading
+excluded). N = 1 runs BASELINE.json configs[1]: M2_Encoder ViT-L/14 + BERT-base bf16, per-GPU batch
+1024, local contrastive; N > 1 keeps 1024 pairs per GPU (weak scaling) and contrasts over the all-gathered global batch
+(configs[2] at N = 8), with DDP's bucketed NCCL gradient all-reduce inside the timed region.
+
+JSON keys beyond the base contract:  roofline (dominant kernel = the tcgen05 GEMM, timed live per launch with CUDA
+events), cpu_baseline (oracle port on the host cores, bounded sample), e2e (public-API call with pinned HOST inputs,
+H2D + loss D2H inside the timed region), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "image-text pairs/sec fwd+bwd"
+FLOP_PER_PAIR = {  # algorithmic fwd+bwd FLOPs per pair, SURVEY.md §8d (GEMMs 24*W^2 + attention 4*L*W per token-layer, x3)
+    "ViT-L-14": 526.0e9,
+    "ViT-B-16": 145.0e9,
+    "ViT-H-14": None,
+}
+
+
+def synth_batch(B, res, L, vocab, seed, device="cpu"):
+    """SURVEY.md §8d synthetic inputs: N(0,1) images; ids with [CLS]=101, [SEP]=102 at the end of a U{8..L} span, [PAD]=0 after."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(B, 3, res, res, generator=g)
+    ids = torch.randint(1, vocab, (B, L), generator=g)
+    ids[:, 0] = 101
+    lens = torch.randint(8, L + 1, (B,), generator=g)
+    pos = torch.arange(L)[None, :]
+    ids[pos == (lens[:, None] - 1)] = 102
+    ids[pos >= lens[:, None]] = 0
+    return image.to(device), ids.to(device)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", 1406.8), d.get("hbm_gbs", 6489.3), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(name, device, ckpt_every):
+    from b200mm.modules import CNCLIP, CONFIGS
+
+    cfg = dict(CONFIGS[name])
+    cfg["text_hidden_dropout_prob"] = 0.0  # the fused kernels implement p = 0; stated in `config.dropout`
+    cfg["text_attention_probs_dropout_prob"] = 0.0
+    torch.manual_seed(0)  # identical weights on every rank
+    model = CNCLIP(**cfg)
+    model = model.to(device).to(torch.bfloat16).train()
+    if ckpt_every > 0:
+        model.visual.set_grad_checkpointing(True, every=ckpt_every)
+    return model, cfg
+
+
+class TrainStep(torch.nn.Module):
+    """The unit DDP wraps: forward = both encoders + fused global contrastive loss."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, image, text):
+        return self.model.contrastive_loss(image, text)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import b200mm
+    from b200mm import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    b200mm._lib.check(b200mm._lib.load().b200mm_check_device(), "b200mm_check_device")
+
+    B, L = args.batch, args.seq_len
+    model, cfg = build_model(args.model, device, args.ckpt_every)
+    res = cfg["image_resolution"]
+    step_mod = TrainStep(model)
+    if world > 1:
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                             static_graph=True)
+    image_h, text_h = synth_batch(B, res, L, cfg["vocab_size"], 1234 + rank)
+    image_h = image_h.to(torch.bfloat16).pin_memory()
+    text_h = text_h.pin_memory()
+    image_d, text_d = image_h.to(device), text_h.to(device)
+
+    def step(img, txt):
+        for p in model.parameters():
+            p.grad = None
+        loss = step_mod(img, txt)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(args.warmup):
+        step(image_d, text_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES = 0
+    ops.GEMM_PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(image_d, text_d)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.LAUNCHES
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    loss_val = float(loss)
+    ms_step = ms_total / args.steps
+    pairs_per_s = B * world / (ms_step * 1e-3)
+
+    # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration, over every launch of the timed region
+    gemm_flops = sum(f for f, _, _, _ in prof)
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b, _ in prof)
+    peak_tf, peak_hbm, peak_src = peaks()
+    gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+
+    # ---------------- end-to-end through the public API with HOST inputs (e2e) ----------------
+    def e2e_step():
+        img = image_h.to(device, non_blocking=True)
+        txt = text_h.to(device, non_blocking=True)
+        ls = step(img, txt)
+        return float(ls)  # device -> host read of the step's result
+
+    e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    e2e_val = B * world / (e2e_ms * 1e-3)
+    peak_mem = torch.cuda.max_memory_allocated(device) / 2**30
+
+    out = None
+    if rank == 0:
+        fpp = FLOP_PER_PAIR.get(args.model)
+        out = {
+            "metric": METRIC, "value": round(pairs_per_s, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (seeded N(0,1) images, random ids with [CLS]/[SEP]/[PAD]; random-init weights, reference init)",
+            "config": {"workload": f"BASELINE.json configs[{1 if world == 1 else 2}]: CNCLIP {args.model} + BERT-base, fwd + fused contrastive loss + bwd",
+                       "model": args.model, "per_gpu_batch": B, "global_batch": B * world, "image_res": res, "seq_len": L,
+                       "parallelism": f"dp{world}" + (" + embedding all-gather / grad reduce-scatter, DDP grad all-reduce in the timed region" if world > 1 else ""),
+                       "dropout": 0.0, "recompute": f"checkpoint every {args.ckpt_every} ViT block(s)" if args.ckpt_every else "none (LN outputs + activated MLP hidden recomputed only)",
+                       "l2_policy": "inputs and activations (>= 0.5 GB per tensor) exceed the 126 MB L2; no flush needed",
+                       "loss": round(loss_val, 5), "peak_mem_gib": round(peak_mem, 1)},
+            "e2e": {"value": round(e2e_val, 2), "unit": "pairs/s", "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": image_h.numel() * 2 + text_h.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all tcgen05 GEMM launches of the timed region)",
+                         "achieved": round(gemm_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(gemm_tf / peak_tf, 4),
+                         "peak_source": peak_src, "launches": len(prof), "share_of_step": round(gemm_ms / ms_total, 4), "traffic": None,
+                         "whole_step_frac": round(pairs_per_s / world * fpp / 1e12 / peak_tf, 4) if fpp else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(args, steps, warmup):
+    """The oracle port (oracle/restated.py, fp32 eager PyTorch on the host cores) on a BOUNDED sample of the workload:
+    same model/config/sequence length, batch `cpu_batch` instead of 1024."""
+    from b200mm.modules import CONFIGS
+    from oracle import restated
+
+    cfg = dict(CONFIGS[args.model])
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    Bc = args.cpu_batch
+    torch.manual_seed(0)
+    from b200mm.modules import CNCLIP
+
+    model = CNCLIP(**cfg)  # parameter container only (reference init); the arithmetic below is the oracle's
+    sd = {k: v.detach().clone().requires_grad_(torch.is_floating_point(v)) for k, v in model.state_dict().items()}
+    del model
+    image, text = synth_batch(Bc, cfg["image_resolution"], args.seq_len, cfg["vocab_size"], 1234)
+    vh = cfg["vision_width"] // cfg.get("vision_head_width", 64)
+    times = []
+    for i in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        _, _, logits, _ = restated.cnclip_forward(sd, image, text, vh, cfg["text_num_attention_heads"])
+        restated.symmetric_info_nce(logits).backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    best = min(times)
+    return {"value": round(Bc / best, 3), "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/restated.py fp32 eager, same model/seq_len, batch {Bc} instead of {args.batch}; best of {steps} step(s) after {warmup} warm-up",
+            "s_per_step": round(best, 2)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host CPU cores. /root/reference (pure Python, needs
+    omegaconf & co to import as a package) does not travel to the GPU box, so the timed object is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"CNCLIP {args.model} + BERT-base fwd + symmetric InfoNCE + bwd, CPU eager fp32, bounded sample batch {args.cpu_batch}",
+                      "model": args.model, "seq_len": args.seq_len},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200mm", choices=["b200mm", "reference"])
+    ap.add_argument("--model", default="ViT-L-14")
+    ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU")
+    ap.add_argument("--seq-len", type=int, default=77)
+    ap.add_argument("--ckpt-every", type=int, default=0, help="re-run every k-th ViT block in backward (0 = never)")
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

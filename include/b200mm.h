@@ -82,6 +82,82 @@ typedef struct {
 int64_t b200mm_gemm_workspace_bytes(int64_t M, int64_t N, int32_t splits);
 int b200mm_gemm_bf16(const b200mm_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (HBM-bound, fp32 statistics).  Replaces LayerNorm.forward (fp32 compute, eps 1e-5)
+ * antmmf/modules/vision/backbone/clip/model.py:213-219 and nn.LayerNorm (eps 1e-12) in
+ * clip/modeling_bert.py:83,179,231 plus their autograd.
+ *   fwd: s = x[row] + add0[row % add_period] + (row % add_period == 0 ? add1 : 0);  y = LN(s)*w + b
+ *        add0/add1 fuse the ViT stem "+ positional_embedding, class_embedding on token 0" (clip/model.py:313-324).
+ *        s_out (optional) receives s; mean/rstd [rows] f32 are saved for backward.
+ *   bwd: dx = LN'(dy) (+ dadd);  dw[W], db[W] f32 are ACCUMULATED with atomics (caller zero-fills).
+ * x, y, s_out, dy, dx, dadd: bf16 [rows, W] contiguous; w, b: bf16 [W]; W % 8 == 0, W <= 2048.
+ * ------------------------------------------------------------------------------------------- */
+int b200mm_layernorm_fwd(const void* x, const void* add0, const void* add1, int64_t add_period, const void* w, const void* b,
+                         void* y, void* s_out, float* mean, float* rstd, int64_t rows, int32_t W, float eps, void* stream);
+int b200mm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* w, const void* dadd,
+                         void* dx, float* dw, float* db, int64_t rows, int32_t W, void* stream);
+
+/* BertEmbeddings.forward, clip/modeling_bert.py:86-103:  y = LN(word[ids] + pos[row % L] + type[type_ids]).
+ * ids/type_ids are int64 device arrays of `rows` entries (bit-exact indexing); s_out gets the bf16 sum. */
+int b200mm_embed_layernorm_fwd(const void* word, const int64_t* ids, const void* pos, int64_t L, const void* type,
+                               const int64_t* type_ids, const void* w, const void* b, void* y, void* s_out, float* mean,
+                               float* rstd, int64_t rows, int32_t W, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head self-attention, forward and backward (S and P never leave the SM).
+ *   ViT : nn.MultiheadAttention in ResidualAttentionBlock.attention, clip/model.py:245-251
+ *   BERT: BertSelfAttention.forward, clip/modeling_bert.py:134-172 (key_bias = (1-mask)*-10000, f32 [B, L])
+ * qkv: bf16 [B, L, ld]; head h of q/k/v at column {q,k,v}_off + h*head_dim.  o: bf16 [B, L, ldo] (head h at h*head_dim).
+ * lse: f32 [B, H, L] (natural log).  head_dim in {32, 64, 80}.  scale = 1/sqrt(head_dim).
+ * bwd writes dq/dk/dv into dqkv (same layout as qkv) and D = rowsum(dO*O) into dsum f32 [B, H, L].
+ * ------------------------------------------------------------------------------------------- */
+int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
+                         const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, void* stream);
+int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o,
+                         int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H,
+                         int32_t L, int32_t head_dim, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Contrastive similarity + log-softmax (tcgen05 GEMM with reduction epilogues).  z[m,n] = alpha * <a_m, b_n>.
+ * Replaces  logit_scale.exp() * I @ T.t()  + cross-entropy (clip/cn_model.py:221-223, dmae_utils.py:528-537),
+ * get_l1_simi_matrix + get_mil_nce_loss (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-226).
+ * a: bf16 [M, K] (this rank's rows), b: bf16 [N, K] (all gathered rows); the positive of row m is column m + diag_off.
+ *   lse_partials: per row and 256-column tile the (max, sum exp) pair, and the diagonal logit   (forward, nothing [M,N] written)
+ *   lse_merge   : partials of one or two blocks -> lse[m]; loss_sum += sum_m (lse[m] - diag[m])
+ *   softgrad    : G[m,n] = alpha * coef * (exp(z - row_lse[m]) - diag_sub*[n == m+diag_off]) as bf16 (dL/d<a_m,b_n>),
+ *                 dscale += sum dL/dz * z (gradient w.r.t. log-temperature); feed G to b200mm_gemm_bf16 for dA, dB.
+ *                 N (a multiple of 8) may include zero padding rows of b: columns >= n_valid get G = 0.
+ * ------------------------------------------------------------------------------------------- */
+int32_t b200mm_contrast_num_tiles(int64_t N);
+int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K, float alpha,
+                                 int64_t diag_off, float* part_max, float* part_sum, float* diag, void* stream);
+int b200mm_contrast_lse_merge(const float* maxA, const float* sumA, int32_t tilesA, const float* maxB, const float* sumB,
+                              int32_t tilesB, const float* diag, int32_t sub_diag, float* lse, float* loss_sum, int64_t M,
+                              void* stream);
+int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K, int64_t n_valid,
+                             float alpha, int64_t diag_off, const float* row_lse, float coef, float diag_sub, int32_t diag_zero,
+                             void* G, int64_t ldg, float* dscale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small HBM-bound helpers.
+ * ------------------------------------------------------------------------------------------- */
+/* y = act(x), bf16, n % 8 == 0 (activation recompute in backward: QuickGELU clip/model.py:222-224, erf-GELU modeling_bert.py:31-37) */
+int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream);
+/* out[(row % period), :] += in[row, :]  (f32 atomics, caller zero-fills): period 1 = bias gradient of nn.Linear,
+ * period L = gradient of positional_embedding (clip/model.py:323) / position_embeddings (modeling_bert.py:97) */
+int b200mm_rowsum_periodic(const void* in, float* out, int64_t rows, int32_t W, int64_t period, void* stream);
+/* out[ids[row], :] += in[row, :] (f32 atomics), rows with ids == skip_id dropped: gradient of nn.Embedding with
+ * padding_idx (modeling_bert.py:71-73) */
+int b200mm_scatter_add_rows(const void* in, const int64_t* ids, float* out, int64_t rows, int32_t W, int64_t skip_id,
+                            int64_t n_out_rows, void* stream);
+int b200mm_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* stream);
+/* y = x / max(||x||, eps) per row (cn_model.py:217-218; F.normalize in univl_video_base.py:114,158) and its backward (dy f32) */
+int b200mm_rownorm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int32_t W, float eps, void* stream);
+int b200mm_rownorm_bwd(const float* dy, const void* x, const float* inv_norm, void* dx, int64_t rows, int32_t W, void* stream);
+/* ViT stem patch extraction for conv1 (kernel == stride == p, no bias; clip/model.py:289-295,310-312):
+ * img bf16 [B, C, H, W] -> out bf16 [B*(Np+1), Kp]; row b*(Np+1) (class-token slot) and columns >= C*p*p are zero. */
+int b200mm_im2row(const void* img, void* out, int64_t B, int32_t C, int32_t H, int32_t W, int32_t p, int32_t Kp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

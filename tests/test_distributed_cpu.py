@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the N > 1 host logic: gather_tensor (row order, differentiable), the padded
+all-gather / reduce-scatter helpers of the contrastive path, and the sharded-loss algebra (each rank owns its rows of
+both logit blocks; W * local share; reduce-scatter of remote-row gradients) against the full-batch oracle."""
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent(
+    """
+    import os, sys
+    sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import b200mm
+    from b200mm.distributed import gather_tensor, get_rank, get_world_size
+    from b200mm.contrastive import _gather_rows, _scatter_grad
+    from oracle import restated
+    assert get_rank() == rank and get_world_size() == world
+
+    # --- gather_tensor: cat order = rank order; backward = sum over ranks of the slice gradient
+    torch.manual_seed(100 + rank)
+    x = torch.randn(3, 5, requires_grad=True)
+    g = gather_tensor(x, method="cat", back_gradient=True)
+    assert g.shape == (3 * world, 5)
+    assert torch.equal(g[3 * rank: 3 * rank + 3], x.detach())
+    wgt = torch.arange(1, 3 * world + 1, dtype=torch.float32)[:, None] * (rank + 1)
+    (g * wgt).sum().backward()
+    expect = sum(torch.arange(1, 3 * world + 1, dtype=torch.float32)[3 * rank: 3 * rank + 3, None] * (r + 1) for r in range(world))
+    assert torch.allclose(x.grad, expect.expand(3, 5)), (x.grad, expect)
+    s = gather_tensor(x.detach(), method="stack")
+    assert s.shape == (world, 3, 5) and not s.requires_grad
+    sc = gather_tensor(torch.tensor(float(rank)))
+    assert sc.tolist() == [float(r) for r in range(world)]
+
+    # --- padded gather / reduce-scatter helpers
+    a = torch.full((3, 4), float(rank + 1))
+    all_a, Bg = _gather_rows(a, None)
+    assert Bg == 3 * world and all_a.shape[0] %% 8 == 0 and torch.equal(all_a[:Bg], torch.cat([torch.full((3, 4), float(r + 1)) for r in range(world)]))
+    assert float(all_a[Bg:].abs().sum()) == 0.0
+    back = _scatter_grad(all_a * (rank + 1), 3, None)
+    assert torch.allclose(back, torch.full((3, 4), float(rank + 1) * sum(r + 1 for r in range(world))))
+
+    # --- sharded contrastive algebra vs the full-batch oracle (fp64 emulation of what the kernels compute per rank)
+    torch.manual_seed(7)
+    B, E, alpha = 4, 6, 9.0
+    I_all = torch.nn.functional.normalize(torch.randn(B * world, E, dtype=torch.float64), dim=-1)
+    T_all = torch.nn.functional.normalize(torch.randn(B * world, E, dtype=torch.float64), dim=-1)
+    I_loc = I_all[rank * B:(rank + 1) * B].clone().requires_grad_()
+    T_loc = T_all[rank * B:(rank + 1) * B].clone().requires_grad_()
+    Ig = gather_tensor(I_loc, method="cat", back_gradient=True)
+    Tg = gather_tensor(T_loc, method="cat", back_gradient=True)
+    A = alpha * I_loc @ Tg.t()
+    Bt = alpha * T_loc @ Ig.t()
+    idx = torch.arange(B) + rank * B
+    local = ((torch.logsumexp(A, 1) - A[torch.arange(B), idx]).sum() + (torch.logsumexp(Bt, 1) - Bt[torch.arange(B), idx]).sum()) / (2 * B * world)
+    (world * local).backward()
+    # oracle: full loss, gradient w.r.t. this rank's rows; DDP would average the per-rank parameter gradients
+    If, Tf = I_all.clone().requires_grad_(), T_all.clone().requires_grad_()
+    full = restated.symmetric_info_nce(alpha * If @ Tf.t())
+    full.backward()
+    tot = torch.tensor([float(world * local)], dtype=torch.float64)
+    dist.all_reduce(tot)
+    assert abs(float(tot) / world - float(full)) < 1e-10
+    assert torch.allclose(I_loc.grad / world, If.grad[rank * B:(rank + 1) * B], atol=1e-12)
+    assert torch.allclose(T_loc.grad / world, Tf.grad[rank * B:(rank + 1) * B], atol=1e-12)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok_{rank}"), "w").write("ok")
+    """
+)
+
+
+def test_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    port = 29500 + (os.getpid() % 400)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
