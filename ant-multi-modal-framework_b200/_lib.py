@@ -88,3 +88,46 @@ def check(rc, what):
     if rc != 0:
         msg = load().b200mm_last_error()
         raise B200mmError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# optional per-call CUDA-event timing of every C-ABI launch (bench.py --profile); off by default, zero overhead when off
+# ---------------------------------------------------------------------------------------------------------------------
+_PROFILE_RECORDS = None
+
+
+def enable_profile(records):
+    """Every compute entry point is wrapped so that (name, start_event, stop_event) is appended to `records`."""
+    global _PROFILE_RECORDS
+    import torch
+
+    lib = load()
+    _PROFILE_RECORDS = records
+    for name in SIGNATURES:
+        if name in ("b200mm_last_error", "b200mm_version", "b200mm_check_device", "b200mm_gemm_workspace_bytes", "b200mm_contrast_num_tiles"):
+            continue
+        raw = getattr(lib, "_raw_" + name, None) or getattr(lib, name)
+        setattr(lib, "_raw_" + name, raw)
+
+        def make(raw_fn, nm):
+            def wrapped(*args):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = raw_fn(*args)
+                e1.record()
+                _PROFILE_RECORDS.append((nm, e0, e1))
+                return rc
+
+            return wrapped
+
+        setattr(lib, name, make(raw, name))
+
+
+def disable_profile():
+    global _PROFILE_RECORDS
+    lib = load()
+    for name in SIGNATURES:
+        raw = getattr(lib, "_raw_" + name, None)
+        if raw is not None:
+            setattr(lib, name, raw)
+    _PROFILE_RECORDS = None

@@ -432,6 +432,10 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const AttnParams p) {
   }
 }
 
+// tcgen05 path (attention_tc.cu): returns 1 if it handled the call, 0 if the shape needs the legacy kernels below
+int attention_fwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
+                     const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, cudaStream_t stream);
+
 static int pick_warps(int L, int max_warps) {
   const int tiles = (L + 15) / 16;
   const int rounds = (tiles + max_warps - 1) / max_warps;
@@ -495,6 +499,8 @@ extern "C" int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, 
   int rc = check_common("attention_fwd", qkv, ld, o, ldo, B, H, L, head_dim, q_off, k_off, v_off);
   if (rc) return rc;
   B200MM_REQUIRE(lse != nullptr, B200MM_ERR_SHAPE, "attention_fwd: lse is required");
+  rc = attention_fwd_tc(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : B200MM_OK;
   AttnParams p{};
   p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv); p.ld = ld; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off;
   p.o = reinterpret_cast<__nv_bfloat16*>(o); p.ldo = ldo; p.lse = lse; p.key_bias = key_bias;

@@ -60,9 +60,9 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 // activations shared by GEMM epilogues and the elementwise kernels
 // QuickGELU  x*sigmoid(1.702x)       (reference: antmmf/modules/vision/backbone/clip/model.py:222-224)
 // erf-GELU   x*0.5*(1+erf(x/sqrt2))  (reference: antmmf/modules/vision/backbone/clip/modeling_bert.py:31-37)
-__device__ __forceinline__ float act_quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_quickgelu(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float dact_quickgelu(float x) {
-  float s = 1.f / (1.f + __expf(-1.702f * x));
+  float s = __fdividef(1.f, 1.f + __expf(-1.702f * x));
   return s * (1.f + 1.702f * x * (1.f - s));
 }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }

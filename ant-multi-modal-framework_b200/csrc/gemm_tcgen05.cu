@@ -11,7 +11,8 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma 128x256x16 (SS operands), accumulators in TMEM,
 //               tcgen05.commit releases smem stages and publishes finished accumulators
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages of 256 fp32 columns)
-//   warps 4..7  epilogue: tcgen05.ld 32 columns at a time -> bias/activation/residual -> 16B global stores;
+//   warps 4..11 epilogue (lane quarter = warp % 4, column half = (warp-4) / 4): tcgen05.ld 32 columns at a time ->
+//               warp-private smem transpose -> bias/activation/residual with row-segment-coalesced 16B global accesses;
 //               runs concurrently with the next tile's mainloop thanks to the double-buffered accumulator
 #include "common.cuh"
 
@@ -27,8 +28,11 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SLAB_BYTES = 64 * BK * 2;  // MN-major operands arrive as 64(mn) x 64(k) slabs of 8 KB
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // +1024: manual 1 KB alignment of the ring
+constexpr int EPI_WARPS = 8;                  // warp e: TMEM lane quarter e % 4, column half e / 4
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr int EPI_STAGE_PITCH = 33;           // fp32 words per staged row (32 columns + 1: conflict-free both ways)
+constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH * 4;  // per epilogue warp
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // +1024: manual 1 KB alignment
 constexpr uint32_t TMEM_COLS = 512;
 
 struct EpiParams {
@@ -115,6 +119,64 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
   }
 }
 
+// Epilogue of the GEMM warps with the extra operands already in registers (software-pipelined loads, see the kernel):
+// `bias8` / `ext8` are the raw bf16x8 vectors of bias[n..n+8) and of the one [M,N] side input (dact_in if set, else residual).
+__device__ __forceinline__ void epi_math_store8(float (&v)[8], int64_t m, int64_t n, const EpiParams& e, const uint4& bias8,
+                                                const uint4& ext8) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= e.alpha;
+  if (e.bias != nullptr) {
+    float2 f0 = unpack_bf16x2(bias8.x), f1 = unpack_bf16x2(bias8.y), f2 = unpack_bf16x2(bias8.z), f3 = unpack_bf16x2(bias8.w);
+    v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+    v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+  }
+  if (e.aux_out != nullptr) {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(e.aux_out + m * e.ldd + n) = o;
+  }
+  float2 x0 = unpack_bf16x2(ext8.x), x1 = unpack_bf16x2(ext8.y), x2 = unpack_bf16x2(ext8.z), x3 = unpack_bf16x2(ext8.w);
+  const float x[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+  if (e.dact_in != nullptr) {
+    if (e.act == B200MM_ACT_QUICKGELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= dact_quickgelu(x[j]);
+    } else if (e.act == B200MM_ACT_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= dact_gelu_erf(x[j]);
+    }
+    if (e.residual != nullptr) {  // rare combination: the residual was not prefetched
+      uint4 r = *reinterpret_cast<const uint4*>(e.residual + m * e.ldr + n);
+      float2 f0 = unpack_bf16x2(r.x), f1 = unpack_bf16x2(r.y), f2 = unpack_bf16x2(r.z), f3 = unpack_bf16x2(r.w);
+      v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+      v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+    }
+  } else {
+    if (e.act == B200MM_ACT_QUICKGELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_quickgelu(v[j]);
+    } else if (e.act == B200MM_ACT_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
+    }
+    if (e.residual != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += x[j];
+    }
+  }
+  if (e.d_f32) {
+    float* d = reinterpret_cast<float*>(e.D) + m * e.ldd + n;
+    *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + m * e.ldd + n) = o;
+  }
+}
+
 struct TileCoord {
   int32_t m_blk, n_blk, split, kb0, kb1;
 };
@@ -155,7 +217,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
     }
     mbar_fence_init();
   }
@@ -237,36 +299,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int ew = warp - 4;
+    const int quarter = ew & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int half = ew >> 2;    // columns [128*half, 128*half+128) of the 256-wide accumulator
+    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ew * (32 * EPI_STAGE_PITCH);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(t, p);
       const int64_t m = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32 + lane;
-      const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN;
+      const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN + half * (BN / 2);
+      // side input of the fused epilogue (dact_in or residual): its 4x16B per lane and chunk are fetched one chunk ahead, the
+      // first chunk even before the accumulator is ready, so their HBM latency overlaps the MMA / the previous chunk's math
+      const int rr = lane >> 2, cg = (lane & 3) * 8;
+      const int64_t m_base = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32;
+      const __nv_bfloat16* ext = nullptr;
+      int64_t ld_ext = 0;
+      uint4 nxt[4];
+      if constexpr (EPI == EPI_STD) {
+        if (p.partial == nullptr) {
+          ext = p.epi.dact_in != nullptr ? p.epi.dact_in : p.epi.residual;
+          ld_ext = p.epi.dact_in != nullptr ? p.epi.ld_dact : p.epi.ldr;
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          nxt[it] = make_uint4(0u, 0u, 0u, 0u);
+          const int64_t mm = m_base + it * 8 + rr;
+          if (ext != nullptr && mm < p.M && n0 + cg < p.N) nxt[it] = *reinterpret_cast<const uint4*>(ext + mm * ld_ext + n0 + cg);
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
       if constexpr (EPI == EPI_STD) {
+        // TMEM gives each thread one row (32 consecutive columns). Going to HBM like that would touch 32 different lines per
+        // warp instruction, so the 32x32 chunk is transposed through a warp-private smem tile: afterwards 4 lanes cover
+        // 64 contiguous bytes of one row and every load/store of the fused epilogue is sector-exact.
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (m < p.M) {
+          __syncwarp();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int64_t n = n0 + c * 32 + g * 8;
-              if (n < p.N) {
+          for (int j = 0; j < 32; ++j) stage[lane * EPI_STAGE_PITCH + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int64_t n = n0 + c * 32 + cg;
+          uint4 cur[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+          if (ext != nullptr && c + 1 < BN / 64) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int64_t mm = m_base + it * 8 + rr;
+              if (mm < p.M && n + 32 < p.N) nxt[it] = *reinterpret_cast<const uint4*>(ext + mm * ld_ext + n + 32);
+            }
+          }
+          if (n < p.N) {
+            uint4 bias8 = make_uint4(0u, 0u, 0u, 0u);
+            if (p.partial == nullptr && p.epi.bias != nullptr) bias8 = *reinterpret_cast<const uint4*>(p.epi.bias + n);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int row = it * 8 + rr;
+              const int64_t mm = m_base + row;
+              if (mm < p.M) {
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                for (int j = 0; j < 8; ++j) v[j] = stage[row * EPI_STAGE_PITCH + cg + j];
                 if (p.partial != nullptr) {
-                  float* d = p.partial + (static_cast<int64_t>(tc.split) * p.M + m) * p.N + n;
+                  float* d = p.partial + (static_cast<int64_t>(tc.split) * p.M + mm) * p.N + n;
                   *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
                   *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 } else {
-                  epi_apply8(v, m, n, p.epi);
+                  epi_math_store8(v, mm, n, p.epi, bias8, cur[it]);
                 }
               }
             }
@@ -277,7 +382,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float mx = -INFINITY, sm = 0.f;
         const int64_t dcol = m + p.con.diag_off;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -304,8 +409,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (m < p.M) {
-          p.con.part_max[m * p.n_tiles + tc.n_blk] = mx;
-          p.con.part_sum[m * p.n_tiles + tc.n_blk] = sm;
+          p.con.part_max[m * (2 * p.n_tiles) + 2 * tc.n_blk + half] = mx;
+          p.con.part_sum[m * (2 * p.n_tiles) + 2 * tc.n_blk + half] = sm;
         }
       } else {
         const float lse = m < p.M ? p.con.row_lse[m] : 0.f;
@@ -313,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float ds_acc = 0.f;
         __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.epi.D) + m * p.epi.ldd;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -532,7 +637,7 @@ static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const 
   return make_tmap_2d_bf16(&tmB, b, K, N, ldb, BK, BN);
 }
 
-extern "C" int32_t b200mm_contrast_num_tiles(int64_t N) { return static_cast<int32_t>(ceil_div(N, BN)); }
+extern "C" int32_t b200mm_contrast_num_tiles(int64_t N) { return static_cast<int32_t>(2 * ceil_div(N, BN)); }  // one partial per 128 columns
 
 extern "C" int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
                                             float alpha, int64_t diag_off, float* part_max, float* part_sum, float* diag,

@@ -125,7 +125,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False
     _lib.check(lib.b200mm_gemm_bf16(ctypes.byref(g), _stream()), "b200mm_gemm_bf16")
     if prof is not None:
         e1.record()
-        prof.append((2.0 * M * N * K, e0, e1, splits))
+        prof.append((2.0 * M * N * K, e0, e1, splits, (M, N, K, int(a_mn), int(b_mn), int(bias is not None), act, int(aux_out),
+                                                       int(dact_in is not None), int(residual is not None), int(out_f32))))
     _count(2 if splits > 1 else 1)
     return (out, aux) if aux_out else out
 

@@ -195,32 +195,36 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.LAUNCHES
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-    loss_val = float(loss)
+    loss_val = float(loss.detach())
     ms_step = ms_total / args.steps
     pairs_per_s = B * world / (ms_step * 1e-3)
 
     # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration, over every launch of the timed region
-    gemm_flops = sum(f for f, _, _, _ in prof)
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b, _ in prof)
+    gemm_flops = sum(r[0] for r in prof)
+    gemm_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
     peak_tf, peak_hbm, peak_src = peaks()
     gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+
+    if args.profile and rank == 0:
+        write_profile(args, prof, step, image_d, text_d, B)
 
     # ---------------- end-to-end through the public API with HOST inputs (e2e) ----------------
     def e2e_step():
         img = image_h.to(device, non_blocking=True)
         txt = text_h.to(device, non_blocking=True)
         ls = step(img, txt)
-        return float(ls)  # device -> host read of the step's result
+        return float(ls.detach())  # device -> host read of the step's result
 
+    e2e_steps = 0 if args.skip_e2e else args.steps
     e2e_step()
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(max(1, e2e_steps)):
         e2e_step()
     t1.record()
     barrier()
-    e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / max(1, e2e_steps)
     e2e_val = B * world / (e2e_ms * 1e-3)
     peak_mem = torch.cuda.max_memory_allocated(device) / 2**30
 
@@ -253,6 +257,37 @@ def run_ours(args):
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out), flush=True)
+
+
+def write_profile(args, gemm_prof, step, image_d, text_d, B):
+    """Per-op CUDA-event breakdown of one extra step + per-shape GEMM table -> gpurun_out/op_profile.json (diagnostics only)."""
+    import b200mm
+    from collections import defaultdict
+
+    recs = []
+    b200mm._lib.enable_profile(recs)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    w0.record()
+    step(image_d, text_d)
+    w1.record()
+    torch.cuda.synchronize()
+    b200mm._lib.disable_profile()
+    by_op = defaultdict(lambda: [0, 0.0])
+    for name, a, b in recs:
+        by_op[name][0] += 1
+        by_op[name][1] += a.elapsed_time(b)
+    shapes = defaultdict(lambda: [0, 0.0, 0.0])
+    for flops, a, b, splits, tag in gemm_prof:
+        k = str(tag + (splits,))
+        shapes[k][0] += 1
+        shapes[k][1] += a.elapsed_time(b)
+        shapes[k][2] += flops
+    table = sorted(((k, n, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0) for k, (n, ms, fl) in shapes.items()), key=lambda r: -r[2])
+    out = {"step_ms_profiled": w0.elapsed_time(w1), "ops": {k: {"calls": v[0], "ms": round(v[1], 3)} for k, v in sorted(by_op.items(), key=lambda kv: -kv[1][1])},
+           "gemm_shapes(M,N,K,a_mn,b_mn,bias,act,aux,dact,res,f32,splits)": [{"shape": k, "calls": n, "ms_total": round(ms, 3), "tflops": round(tf, 1)} for k, n, ms, tf in table]}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"op_profile_b{B}.json"), "w"), indent=1)
 
 
 def cpu_baseline(args, steps, warmup):
@@ -317,6 +352,8 @@ def main():
     ap.add_argument("--ckpt-every", type=int, default=0, help="re-run every k-th ViT block in backward (0 = never)")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="write gpurun_out/op_profile_b<B>.json (per-op CUDA-event breakdown)")
+    ap.add_argument("--skip-e2e", action="store_true", help="diagnostics only: skip the host-input leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
