@@ -436,6 +436,10 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const AttnParams p) {
 int attention_fwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
                      const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, cudaStream_t stream);
 
+int attention_bwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o, int64_t ldo,
+                     const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H, int32_t L, int32_t head_dim,
+                     float scale, cudaStream_t stream);
+
 static int pick_warps(int L, int max_warps) {
   const int tiles = (L + 15) / 16;
   const int rounds = (tiles + max_warps - 1) / max_warps;
@@ -516,6 +520,9 @@ extern "C" int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, 
   B200MM_REQUIRE(lse && d_o && dqkv && dsum, B200MM_ERR_SHAPE, "attention_bwd: null pointer");
   B200MM_REQUIRE((reinterpret_cast<uintptr_t>(d_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, B200MM_ERR_ALIGN,
                  "attention_bwd: d_o/dqkv must be 16B aligned");
+  rc = attention_bwd_tc(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale,
+                        reinterpret_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : B200MM_OK;
   AttnParams p{};
   p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv); p.ld = ld; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off;
   p.o = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(o)); p.ldo = ldo;

@@ -7,11 +7,12 @@
 //   persistent CTA (one per SM) loops over (batch, head) items; per item K and V ([L,64] each) are TMA-loaded once into
 //   128B-swizzled smem and the queries are processed in 128-row tiles:
 //     S = Q_tile K^T     tcgen05.mma 128 x Lk x 64 (SS), fp32 S in TMEM (Lk <= 320 columns)
-//     softmax            4 warps, thread == row == TMEM lane: two passes over S with tcgen05.ld (no cross-thread
-//                        reductions), P written as bf16 into K-major swizzled smem tiles
+//     softmax            16 warps (4 per scheduler to hide TMEM/MUFU latency): warp = (TMEM lane quarter, column partition);
+//                        two passes over S with tcgen05.ld, row max/sum combined through smem, P written as bf16 into
+//                        K-major swizzled smem tiles
 //     O = P V            tcgen05.mma 128 x 64 x Lk, V read MN-major from the same [key][64] smem image
 //     epilogue           O * 1/rowsum -> bf16 -> smem transpose -> coalesced stores; LSE per row
-//   warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = softmax/epilogue.
+//   warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..19 = softmax/epilogue.
 //   K/V/Q loads of the next tile/item run ahead through mbarrier rings; QK^T of tile t+1 overlaps the epilogue of t.
 #include "common.cuh"
 
@@ -22,7 +23,9 @@
 namespace b200mm {
 
 constexpr int AT_HD = 64;
-constexpr int AT_THREADS = 256;
+constexpr int AT_SM_WARPS = 16;               // softmax warps: TMEM lane quarter = w % 4, column partition = w / 4
+constexpr int AT_SM_THREADS = AT_SM_WARPS * 32;
+constexpr int AT_THREADS = 128 + AT_SM_THREADS;
 constexpr int AT_MAX_LK = 320;
 constexpr float AT_LOG2E = 1.4426950408889634f;
 
@@ -55,6 +58,10 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+// Order in which an item's query tiles are processed: the last tile (the short remainder, e.g. 1 row of 257) goes second, so
+// that the item ENDS with a full tile whose softmax hides the TMA latency of the next item's K / Q loads.
+__device__ __forceinline__ int tile_order(int k, int n) { return n < 3 ? k : (k == 0 ? 0 : (k == 1 ? n - 1 : k - 1)); }
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows][128 B] tile with the 128B swizzle
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
@@ -64,7 +71,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t tmem_base_smem;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1 KB alignment for the 128B swizzle; offset arithmetic on the __shared__ array keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int Lk = p.Lk;
   const int kv_bytes = Lk * 128;                     // one [Lk][64] bf16 image
   const int kv_pad = (kv_bytes + 1023) & ~1023;
@@ -74,6 +82,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* q_sm = v_sm + kv_pad;                     // 2 x 16 KB
   uint8_t* p_sm = q_sm + 2 * 16384;                  // n_ptiles x 16 KB
   float* bias_sm = reinterpret_cast<float*>(p_sm + n_ptiles * 16384);  // [Lk] key bias * log2e, -inf for key >= L
+  float* red_max = bias_sm + Lk;       // [4][128] per-partition row maxima
+  float* red_sum = red_max + 4 * 128;  // [4][128] per-partition row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -81,7 +91,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmKV);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) mbar_init(&bars[i], (i == BAR_P_FULL || i == BAR_O_EMPTY) ? 128 : 1);
+    for (int i = 0; i < BAR_COUNT; ++i) mbar_init(&bars[i], (i == BAR_P_FULL || i == BAR_O_EMPTY) ? AT_SM_THREADS : 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -102,8 +112,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt) {
       const int b = item / p.H, h = item - b * p.H;
       const int32_t row0 = b * p.L;
-      for (int t = 0; t < n_qt; ++t, ++tile_cnt) {
-        if (t == 0) {
+      for (int tk = 0; tk < n_qt; ++tk, ++tile_cnt) {
+        const int t = tile_order(tk, n_qt);
+        if (tk == 0) {
           mbar_wait(&bars[BAR_K_EMPTY], (item_cnt & 1) ^ 1);
           if (lane == 0) {
             mbar_expect_tx(&bars[BAR_K_FULL], kv_bytes);
@@ -117,7 +128,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_expect_tx(&bars[BAR_Q_FULL0 + qb], 16384);
           tma_load_2d(&tmQ, &bars[BAR_Q_FULL0 + qb], q_sm + qb * 16384, p.q_off + h * AT_HD, row0 + t * 128);
         }
-        if (t == 0) {
+        if (tk == 0) {
           mbar_wait(&bars[BAR_V_EMPTY], (item_cnt & 1) ^ 1);
           if (lane == 0) {
             mbar_expect_tx(&bars[BAR_V_FULL], kv_bytes);
@@ -135,10 +146,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t idesc_pv = make_idesc_bf16(128, AT_HD, 0, 1);  // A = P K-major, B = V MN-major
     uint32_t item_cnt = 0, tile_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt) {
-      for (int t = 0; t < n_qt; ++t, ++tile_cnt) {
+      for (int tk = 0; tk < n_qt; ++tk, ++tile_cnt) {
         const int qb = tile_cnt & 1;
         mbar_wait(&bars[BAR_Q_FULL0 + qb], (tile_cnt >> 1) & 1);
-        if (t == 0) mbar_wait(&bars[BAR_K_FULL], item_cnt & 1);
+        if (tk == 0) mbar_wait(&bars[BAR_K_FULL], item_cnt & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t qa = smem_u32(q_sm + qb * 16384), kb = smem_u32(k_sm);
@@ -150,11 +161,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           umma_commit(&bars[BAR_S_FULL]);
           umma_commit(&bars[BAR_Q_EMPTY0 + qb]);
-          if (t == n_qt - 1) umma_commit(&bars[BAR_K_EMPTY]);
+          if (tk == n_qt - 1) umma_commit(&bars[BAR_K_EMPTY]);
         }
         __syncwarp();
         mbar_wait(&bars[BAR_P_FULL], tile_cnt & 1);
-        if (t == 0) mbar_wait(&bars[BAR_V_FULL], item_cnt & 1);
+        if (tk == 0) mbar_wait(&bars[BAR_V_FULL], item_cnt & 1);
         mbar_wait(&bars[BAR_O_EMPTY], (tile_cnt & 1) ^ 1);
         tc_fence_after();
         if (lane == 0) {
@@ -166,133 +177,141 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             umma_bf16(tmem_o, adesc, bdesc, idesc_pv, kk > 0);
           }
           umma_commit(&bars[BAR_O_FULL]);
-          if (t == n_qt - 1) umma_commit(&bars[BAR_V_EMPTY]);
+          if (tk == n_qt - 1) umma_commit(&bars[BAR_V_EMPTY]);
         }
         __syncwarp();
       }
     }
   } else if (warp >= 4) {
-    // ===================== softmax + epilogue (thread == query row == TMEM lane) =====================
+    // ===================== softmax + epilogue =====================
+    // 16 warps: warp sw owns TMEM lanes / query rows [32*(sw%4), +32) and the 16-column chunks cc with cc % 4 == sw / 4.
+    // (One warp per scheduler cannot hide the TMEM / MUFU / ALU latencies: 4 per scheduler can.)
     const int sw = warp - 4;
-    const int r = sw * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(sw * 32) << 16;
+    const int quarter = sw & 3, part = sw >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale * AT_LOG2E;
+    const int n_chunks = Lk / 16;
+    const bool has_bias = p.key_bias != nullptr;
     uint32_t tile_cnt = 0;
+    auto sm_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory"); };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.H, h = item - b * p.H;
-      // key bias of this batch row (shared by its H heads, but items of one CTA are strided, so reload per item)
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers are done with bias_sm
-      for (int i = threadIdx.x - 128; i < Lk; i += 128)
-        bias_sm[i] = i < p.L ? (p.key_bias ? p.key_bias[static_cast<int64_t>(b) * p.L + i] * AT_LOG2E : 0.f) : -INFINITY;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int t = 0; t < n_qt; ++t, ++tile_cnt) {
+      sm_sync();  // previous item's readers are done with bias_sm
+      for (int i = threadIdx.x - 128; i < Lk; i += AT_SM_THREADS)
+        bias_sm[i] = i < p.L ? (has_bias ? p.key_bias[static_cast<int64_t>(b) * p.L + i] * AT_LOG2E : 0.f) : -INFINITY;
+      sm_sync();
+      for (int tk = 0; tk < n_qt; ++tk, ++tile_cnt) {
+        const int t = tile_order(tk, n_qt);
         const int q_row = t * 128 + r;
-        const bool warp_active = t * 128 + sw * 32 < p.L;  // warp-uniform: any valid row in this warp
+        const bool warp_active = t * 128 + quarter * 32 < p.L;  // warp-uniform: any valid row in this warp
         mbar_wait(&bars[BAR_S_FULL], tile_cnt & 1);
         tc_fence_after();
-        float mx = -INFINITY, sum = 0.f;
+        // ---- pass 1: partial row maximum of s*c + bias over this warp's chunks
+        float mx = -INFINITY;
         if (warp_active) {
-          // pass 1: row maximum of s*c + bias
-          for (int j0 = 0; j0 < Lk; j0 += 32) {
-            if (j0 + 32 <= Lk) {
-              uint32_t v[32];
-              tmem_ld_32x32(tmem_s + lane_addr + j0, v);
-              tmem_ld_wait();
+          float m0 = -INFINITY, m1 = -INFINITY;
+          auto pass1 = [&](const uint32_t (&v)[16], int cc) {
+            if (has_bias || cc * 16 + 16 > p.L) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), c, bias_sm[j0 + j]));
-            } else {
-              uint32_t v[16];
-              tmem_ld_32x16(tmem_s + lane_addr + j0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), c, bias_sm[j0 + j]));
-            }
-          }
-          // pass 2: p = exp2(s*c + bias - mx) -> bf16 -> K-major swizzled P tiles
-          for (int j0 = 0; j0 < Lk; j0 += 32) {
-            uint8_t* ptile = p_sm + (j0 >> 6) * 16384;
-            const int chunk0 = (j0 & 63) >> 3;
-            if (j0 + 32 <= Lk) {
-              uint32_t v[32];
-              tmem_ld_32x32(tmem_s + lane_addr + j0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float e[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  e[j] = fast_exp2(fmaf(__uint_as_float(v[g * 8 + j]), c, bias_sm[j0 + g * 8 + j]) - mx);
-                  sum += e[j];
-                }
-                uint4 o;
-                o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
-                o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
-                *reinterpret_cast<uint4*>(ptile + sw128_off(r, chunk0 + g)) = o;
+              for (int j = 0; j < 16; j += 2) {
+                m0 = fmaxf(m0, fmaf(__uint_as_float(v[j]), c, bias_sm[cc * 16 + j]));
+                m1 = fmaxf(m1, fmaf(__uint_as_float(v[j + 1]), c, bias_sm[cc * 16 + j + 1]));
               }
             } else {
-              uint32_t v[16];
-              tmem_ld_32x16(tmem_s + lane_addr + j0, v);
-              tmem_ld_wait();
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                float e[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  e[j] = fast_exp2(fmaf(__uint_as_float(v[g * 8 + j]), c, bias_sm[j0 + g * 8 + j]) - mx);
-                  sum += e[j];
-                }
-                uint4 o;
-                o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
-                o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
-                *reinterpret_cast<uint4*>(ptile + sw128_off(r, chunk0 + g)) = o;
+              for (int j = 0; j < 16; j += 2) {
+                m0 = fmaxf(m0, __uint_as_float(v[j]) * c);
+                m1 = fmaxf(m1, __uint_as_float(v[j + 1]) * c);
               }
             }
+          };
+          for (int cc = part; cc < n_chunks; cc += 4) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_s + lane_addr + cc * 16, v);
+            tmem_ld_wait16(v);
+            pass1(v, cc);
           }
+          red_max[part * 128 + r] = fmaxf(m0, m1);
+        }
+        sm_sync();
+        float sum = 0.f;
+        if (warp_active) {
+          mx = fmaxf(fmaxf(red_max[r], red_max[128 + r]), fmaxf(red_max[256 + r], red_max[384 + r]));
+          // ---- pass 2: p = exp2(s*c + bias - mx) -> bf16 -> K-major swizzled P tiles (this warp's chunks)
+          float s0 = 0.f, s1 = 0.f;
+          auto pass2 = [&](const uint32_t (&v)[16], int cc) {
+            float e[16];
+            if (has_bias || cc * 16 + 16 > p.L) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), c, bias_sm[cc * 16 + j]) - mx);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), c, -mx));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) { s0 += e[j]; s1 += e[j + 1]; }
+            uint8_t* ptile = p_sm + (cc >> 2) * 16384;
+            const int chunk0 = (cc & 3) * 2;
+            uint4 o;
+            o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+            o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(ptile + sw128_off(r, chunk0)) = o;
+            o.x = pack_bf16x2(e[8], e[9]); o.y = pack_bf16x2(e[10], e[11]);
+            o.z = pack_bf16x2(e[12], e[13]); o.w = pack_bf16x2(e[14], e[15]);
+            *reinterpret_cast<uint4*>(ptile + sw128_off(r, chunk0 + 1)) = o;
+          };
+          for (int cc = part; cc < n_chunks; cc += 4) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_s + lane_addr + cc * 16, v);
+            tmem_ld_wait16(v);
+            pass2(v, cc);
+          }
+          red_sum[part * 128 + r] = s0 + s1;
         }
         // make the generic-proxy smem writes visible to the tensor core (async proxy), release S, publish P
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bars[BAR_P_FULL]);
-        // ---- epilogue: O / sum -> bf16, transposed through this warp's 32 rows of P tile 0 (free once PV has completed)
+        sm_sync();  // red_sum complete
+        if (warp_active) sum = (red_sum[r] + red_sum[128 + r]) + (red_sum[256 + r] + red_sum[384 + r]);
+        // ---- epilogue: O / sum -> bf16; partition `part` converts O columns [16*part, +16) of its rows, staged in P tile 0
+        //      (free once PV has completed), then all 16 warps write the tile out with coalesced 128-byte rows
         mbar_wait(&bars[BAR_O_FULL], tile_cnt & 1);
         tc_fence_after();
         if (warp_active) {
           const float inv = 1.f / sum;
-          uint8_t* otile = p_sm;  // [128][128 B] swizzled, rows sw*32 .. +31 belong to this warp
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_o + lane_addr + half * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
-              o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
-              o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
-              o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
-              *reinterpret_cast<uint4*>(otile + sw128_off(r, half * 4 + g)) = o;
-            }
-          }
-          if (q_row < p.L) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.L + q_row] = (mx + log2f(sum)) / AT_LOG2E;
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_o + lane_addr + part * 16, v);
+          tmem_ld_wait16(v);
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+          *reinterpret_cast<uint4*>(p_sm + sw128_off(r, part * 2)) = o;
+          o.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+          *reinterpret_cast<uint4*>(p_sm + sw128_off(r, part * 2 + 1)) = o;
+          if (part == 0 && q_row < p.L) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.L + q_row] = (mx + log2f(sum)) / AT_LOG2E;
         }
         tc_fence_before();
         mbar_arrive(&bars[BAR_O_EMPTY]);
-        if (warp_active) {
-          __syncwarp();
-          // 8 lanes x 16 B = one 128-byte output row; 4 rows per warp instruction
+        sm_sync();  // staged O tile complete
+        {
+          // 8 lanes x 16 B = one 128-byte output row; warp sw writes rows [8*sw, 8*sw+8)
           __nv_bfloat16* obase = p.o + (static_cast<int64_t>(b) * p.L + t * 128) * p.ldo + h * AT_HD;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = sw * 32 + it * 4 + (lane >> 3);
+          for (int it = 0; it < 2; ++it) {
+            const int row = sw * 8 + it * 4 + (lane >> 3);
             const int ch = lane & 7;
             if (t * 128 + row < p.L)
               *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * p.ldo + ch * 8) = *reinterpret_cast<const uint4*>(p_sm + sw128_off(row, ch));
           }
-          __syncwarp();
         }
-        // the next tile's P stores reuse p_sm: all 4 warps must have finished reading their staged O rows. P tile 0 rows are
-        // warp-private in both uses (rows sw*32..+31), so a warp-level sync above is sufficient.
+        sm_sync();  // staged tile consumed before the next tile's P stores overwrite it
       }
     }
   }
@@ -308,7 +327,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 static size_t attn_tc_smem_bytes(int Lk) {
   const int kv_pad = (Lk * 128 + 1023) & ~1023;
   const int n_ptiles = (Lk + 63) / 64;
-  return static_cast<size_t>(2) * kv_pad + 2 * 16384 + static_cast<size_t>(n_ptiles) * 16384 + Lk * 4 + 1024;
+  return static_cast<size_t>(2) * kv_pad + 2 * 16384 + static_cast<size_t>(n_ptiles) * 16384 + Lk * 4 + 2 * 4 * 128 * 4 + 1024;
 }
 
 // returns 1 if handled, 0 if the shape is not supported by the tcgen05 path (caller falls back), <0 on error
@@ -335,6 +354,365 @@ int attention_fwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
   const int grid = std::min(B * H, sm_count());
   attn_fwd_tc_kernel<<<grid, AT_THREADS, smem, stream>>>(tmQ, tmKV, p);
   rc = check_launch("attn_fwd_tc_kernel");
+  return rc ? rc : 1;
+}
+
+
+// =====================================================================================================================
+// backward: one kernel per (batch, head) item producing dQ, dK, dV (no recomputation pass, no atomics)
+//
+//   key tiles j (128 keys = MMA M / TMEM lanes)  x  query chunks i (<= 96 queries = TMEM columns):
+//     S^T_ji = K_j Q_i^T,  dP^T_ji = V_j dO_i^T                      tcgen05, fp32 in TMEM
+//     P^T = exp2(S^T c + bias_key - lse_q),  dS^T = P^T (dP^T - D_q) scale     16 elementwise warps, bf16 tiles in smem
+//     dV_j += P^T dO_i,  dK_j += dS^T Q_i                               A = the K-major smem tiles
+//     dQ_i += dS_ji K_j                                                 A = the SAME dS^T tile read MN-major (transposed view)
+//   TMEM (512 columns, exactly full): S^T 96 | dP^T 96 | dV 64 | dK 64 | dQ_0..2 3x64.
+//   Q and dO of the item stay resident in smem ([Lq][64] images, used K-major for S^T/dP^T and MN-major for dK/dV);
+//   K_j / V_j tiles are double-buffered.
+// =====================================================================================================================
+constexpr int AB_CW = 96;  // query-chunk width (TMEM columns of S^T / dP^T)
+
+struct AttnBwdTcParams {
+  const float* lse;
+  const float* dsum;
+  const float* key_bias;
+  __nv_bfloat16* dqkv;
+  int64_t ld;
+  int32_t B, H, L, Lq;
+  int32_t q_off, k_off, v_off;
+  float scale;
+};
+
+enum { BB_QD_FULL = 0, BB_QD_EMPTY, BB_KV_FULL0, BB_KV_FULL1, BB_KV_EMPTY0, BB_KV_EMPTY1, BB_SD_FULL, BB_PDS_FULL, BB_PDS_EMPTY,
+       BB_DKV_FULL, BB_DKV_EMPTY, BB_DQ_FULL, BB_DQ_EMPTY, BB_COUNT };
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQrows, const __grid_constant__ CUtensorMap tmQtile,
+                   const __grid_constant__ CUtensorMap tmDOrows, const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[BB_COUNT];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int Lq = p.Lq;
+  const int img_bytes = Lq * 128;
+  const int img_pad = (img_bytes + 1023) & ~1023;
+  uint8_t* q_sm = smem;                    // [Lq][64] Q image
+  uint8_t* do_sm = q_sm + img_pad;         // [Lq][64] dO image
+  uint8_t* k_sm = do_sm + img_pad;         // 2 x [128][64]
+  uint8_t* v_sm = k_sm + 2 * 16384;        // 2 x [128][64]
+  uint8_t* pt_sm = v_sm + 2 * 16384;       // P^T  : 2 sub-tiles [128 keys][64 queries]
+  uint8_t* ds_sm = pt_sm + 2 * 16384;      // dS^T : 2 sub-tiles
+  float* lse_sm = reinterpret_cast<float*>(ds_sm + 2 * 16384);  // [Lq] lse * log2e (+inf for q >= L)
+  float* d_sm = lse_sm + Lq;                                      // [Lq] D (0 for q >= L)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQrows);
+    tma_prefetch_desc(&tmQtile);
+    tma_prefetch_desc(&tmDOrows);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < BB_COUNT; ++i)
+      mbar_init(&bars[i], (i == BB_PDS_FULL || i == BB_DKV_EMPTY || i == BB_DQ_EMPTY) ? AT_SM_THREADS : 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 96, tm_dv = tmem_base + 192, tm_dk = tmem_base + 256, tm_dq = tmem_base + 320;
+
+  const int n_items = p.B * p.H;
+  const int n_kt = (p.L + 127) / 128;
+  const int n_qc = (Lq + AB_CW - 1) / AB_CW;  // <= 3
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t item_cnt = 0, tile_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt) {
+      const int b = item / p.H, h = item - b * p.H;
+      const int32_t row0 = b * p.L;
+      mbar_wait(&bars[BB_QD_EMPTY], (item_cnt & 1) ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(&bars[BB_QD_FULL], 2 * img_bytes);
+        tma_load_2d(&tmQrows, &bars[BB_QD_FULL], q_sm, p.q_off + h * AT_HD, row0);
+        tma_load_2d(&tmQrows, &bars[BB_QD_FULL], q_sm + img_bytes / 2, p.q_off + h * AT_HD, row0 + Lq / 2);
+        tma_load_2d(&tmDOrows, &bars[BB_QD_FULL], do_sm, h * AT_HD, row0);
+        tma_load_2d(&tmDOrows, &bars[BB_QD_FULL], do_sm + img_bytes / 2, h * AT_HD, row0 + Lq / 2);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kt; ++j, ++tile_cnt) {
+        const int jb = tile_cnt & 1;
+        mbar_wait(&bars[BB_KV_EMPTY0 + jb], ((tile_cnt >> 1) & 1) ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&bars[BB_KV_FULL0 + jb], 2 * 16384);
+          tma_load_2d(&tmQtile, &bars[BB_KV_FULL0 + jb], k_sm + jb * 16384, p.k_off + h * AT_HD, row0 + j * 128);
+          tma_load_2d(&tmQtile, &bars[BB_KV_FULL0 + jb], v_sm + jb * 16384, p.v_off + h * AT_HD, row0 + j * 128);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_acc = make_idesc_bf16(128, AT_HD, 0, 1);  // dV / dK : A K-major (P^T, dS^T), B MN-major (dO, Q)
+    const uint32_t idesc_dq = make_idesc_bf16(128, AT_HD, 1, 1);   // dQ      : A = dS^T read MN-major, B = K_j MN-major
+    uint32_t item_cnt = 0, tile_cnt = 0, step_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt) {
+      mbar_wait(&bars[BB_QD_FULL], item_cnt & 1);
+      mbar_wait(&bars[BB_DQ_EMPTY], (item_cnt & 1) ^ 1);  // previous item's dQ accumulators have been read out
+      for (int j = 0; j < n_kt; ++j, ++tile_cnt) {
+        const int jb = tile_cnt & 1;
+        mbar_wait(&bars[BB_KV_FULL0 + jb], (tile_cnt >> 1) & 1);
+        const uint32_t ka = smem_u32(k_sm + jb * 16384), va = smem_u32(v_sm + jb * 16384);
+        for (int i = 0; i < n_qc; ++i, ++step_cnt) {
+          const int q0 = i * AB_CW;
+          const int w = min(AB_CW, Lq - q0);
+          const uint32_t idesc_sd = make_idesc_bf16(128, w, 0, 0);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t qb = smem_u32(q_sm) + q0 * 128, dob = smem_u32(do_sm) + q0 * 128;
+#pragma unroll
+            for (int k = 0; k < AT_HD / 16; ++k) {
+              umma_bf16(tm_s, make_smem_desc_sw128(ka + k * 32, 16, 1024), make_smem_desc_sw128(qb + k * 32, 16, 1024), idesc_sd, k > 0);
+              umma_bf16(tm_dp, make_smem_desc_sw128(va + k * 32, 16, 1024), make_smem_desc_sw128(dob + k * 32, 16, 1024), idesc_sd, k > 0);
+            }
+            umma_commit(&bars[BB_SD_FULL]);
+          }
+          __syncwarp();
+          mbar_wait(&bars[BB_PDS_FULL], step_cnt & 1);
+          if (i == 0) mbar_wait(&bars[BB_DKV_EMPTY], (tile_cnt & 1) ^ 1);  // previous tile's dV/dK have been read out
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t pa = smem_u32(pt_sm), dsa = smem_u32(ds_sm);
+            const uint32_t qb = smem_u32(q_sm) + q0 * 128, dob = smem_u32(do_sm) + q0 * 128;
+            for (int kk = 0; kk < w / 16; ++kk) {
+              const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
+              umma_bf16(tm_dv, make_smem_desc_sw128(pa + aoff, 16, 1024), make_smem_desc_sw128(dob + kk * 2048, 8192, 1024), idesc_acc,
+                        (i > 0 || kk > 0));
+              umma_bf16(tm_dk, make_smem_desc_sw128(dsa + aoff, 16, 1024), make_smem_desc_sw128(qb + kk * 2048, 8192, 1024), idesc_acc,
+                        (i > 0 || kk > 0));
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)  // reduction over the 128 keys of tile j
+              umma_bf16(tm_dq + i * 64, make_smem_desc_sw128(dsa + kk * 2048, 16384, 1024), make_smem_desc_sw128(ka + kk * 2048, 8192, 1024),
+                        idesc_dq, (j > 0 || kk > 0));
+            umma_commit(&bars[BB_PDS_EMPTY]);
+            if (i == n_qc - 1) {
+              umma_commit(&bars[BB_DKV_FULL]);
+              umma_commit(&bars[BB_KV_EMPTY0 + jb]);
+              if (j == n_kt - 1) {
+                umma_commit(&bars[BB_DQ_FULL]);
+                umma_commit(&bars[BB_QD_EMPTY]);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== elementwise + epilogues (16 warps) =====================
+    const int sw = warp - 4;
+    const int quarter = sw & 3, part = sw >> 2;
+    const int r = quarter * 32 + lane;  // key row inside the tile / TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const float c = p.scale * AT_LOG2E;
+    uint32_t item_cnt = 0, tile_cnt = 0, step_cnt = 0;
+    auto sm_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory"); };
+    // staged-tile writer: 16 fp32 accumulator columns [16*part, +16) of row r -> bf16 into a swizzled [128][128 B] tile
+    auto stage16 = [&](uint8_t* tile, const uint32_t (&v)[16]) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1])); o.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+      o.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5])); o.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+      *reinterpret_cast<uint4*>(tile + sw128_off(r, part * 2)) = o;
+      o.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9])); o.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+      o.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13])); o.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+      *reinterpret_cast<uint4*>(tile + sw128_off(r, part * 2 + 1)) = o;
+    };
+    // coalesced write-out of a staged tile: warp sw writes rows [8*sw, +8), 8 lanes x 16 B per 128-byte row
+    auto write_tile = [&](const uint8_t* tile, __nv_bfloat16* gbase, int rows_valid) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = sw * 8 + it * 4 + (lane >> 3);
+        const int ch = lane & 7;
+        if (row < rows_valid)
+          *reinterpret_cast<uint4*>(gbase + static_cast<int64_t>(row) * p.ld + ch * 8) = *reinterpret_cast<const uint4*>(tile + sw128_off(row, ch));
+      }
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt) {
+      const int b = item / p.H, h = item - b * p.H;
+      const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+      sm_sync();  // previous item's readers are done with lse_sm / d_sm
+      for (int i = threadIdx.x - 128; i < Lq; i += AT_SM_THREADS) {
+        lse_sm[i] = i < p.L ? p.lse[bh * p.L + i] * AT_LOG2E : INFINITY;
+        d_sm[i] = i < p.L ? p.dsum[bh * p.L + i] : 0.f;
+      }
+      sm_sync();
+      for (int j = 0; j < n_kt; ++j, ++tile_cnt) {
+        const int key = j * 128 + r;
+        const bool warp_active = j * 128 + quarter * 32 < p.L;
+        const float kb = key < p.L ? (p.key_bias ? p.key_bias[static_cast<int64_t>(b) * p.L + key] * AT_LOG2E : 0.f) : -INFINITY;
+        for (int i = 0; i < n_qc; ++i, ++step_cnt) {
+          const int q0 = i * AB_CW;
+          const int w = min(AB_CW, Lq - q0);
+          mbar_wait(&bars[BB_SD_FULL], step_cnt & 1);
+          mbar_wait(&bars[BB_PDS_EMPTY], (step_cnt & 1) ^ 1);  // previous step's MMAs no longer read the P^T / dS^T tiles
+          tc_fence_after();
+          for (int cc = part; cc < w / 16; cc += 4) {
+            uint8_t* pt = pt_sm + (cc >> 2) * 16384;
+            uint8_t* dt = ds_sm + (cc >> 2) * 16384;
+            const int ch0 = (cc & 3) * 2;
+            if (warp_active) {
+              uint32_t sv[16], dv[16];
+              tmem_ld_32x16(tm_s + lane_addr + cc * 16, sv);
+              tmem_ld_32x16(tm_dp + lane_addr + cc * 16, dv);
+              tmem_ld_wait16(sv);
+              tmem_ld_wait16(dv);
+              float pe[16], de[16];
+#pragma unroll
+              for (int x = 0; x < 16; ++x) {
+                const int q = q0 + cc * 16 + x;
+                pe[x] = fast_exp2(fmaf(__uint_as_float(sv[x]), c, kb) - lse_sm[q]);
+                de[x] = pe[x] * (__uint_as_float(dv[x]) - d_sm[q]) * p.scale;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(pe[0], pe[1]); o.y = pack_bf16x2(pe[2], pe[3]); o.z = pack_bf16x2(pe[4], pe[5]); o.w = pack_bf16x2(pe[6], pe[7]);
+              *reinterpret_cast<uint4*>(pt + sw128_off(r, ch0)) = o;
+              o.x = pack_bf16x2(pe[8], pe[9]); o.y = pack_bf16x2(pe[10], pe[11]); o.z = pack_bf16x2(pe[12], pe[13]); o.w = pack_bf16x2(pe[14], pe[15]);
+              *reinterpret_cast<uint4*>(pt + sw128_off(r, ch0 + 1)) = o;
+              o.x = pack_bf16x2(de[0], de[1]); o.y = pack_bf16x2(de[2], de[3]); o.z = pack_bf16x2(de[4], de[5]); o.w = pack_bf16x2(de[6], de[7]);
+              *reinterpret_cast<uint4*>(dt + sw128_off(r, ch0)) = o;
+              o.x = pack_bf16x2(de[8], de[9]); o.y = pack_bf16x2(de[10], de[11]); o.z = pack_bf16x2(de[12], de[13]); o.w = pack_bf16x2(de[14], de[15]);
+              *reinterpret_cast<uint4*>(dt + sw128_off(r, ch0 + 1)) = o;
+            } else {
+              // keys >= L: rows of dS^T must be exactly zero (they are reduced over in dQ); P^T rows only feed unused dV rows
+              const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(pt + sw128_off(r, ch0)) = z;
+              *reinterpret_cast<uint4*>(pt + sw128_off(r, ch0 + 1)) = z;
+              *reinterpret_cast<uint4*>(dt + sw128_off(r, ch0)) = z;
+              *reinterpret_cast<uint4*>(dt + sw128_off(r, ch0 + 1)) = z;
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&bars[BB_PDS_FULL]);
+        }
+        // ---- tile epilogue: dV_j, dK_j -> bf16 rows of dqkv (staged through the now idle P^T / dS^T sub-tile 0)
+        mbar_wait(&bars[BB_DKV_FULL], tile_cnt & 1);
+        tc_fence_after();
+        if (warp_active) {
+          uint32_t a[16], bq[16];
+          tmem_ld_32x16(tm_dv + lane_addr + part * 16, a);
+          tmem_ld_32x16(tm_dk + lane_addr + part * 16, bq);
+          tmem_ld_wait16(a);
+          tmem_ld_wait16(bq);
+          stage16(pt_sm, a);
+          stage16(ds_sm, bq);
+        }
+        tc_fence_before();
+        mbar_arrive(&bars[BB_DKV_EMPTY]);
+        sm_sync();
+        {
+          __nv_bfloat16* gk = p.dqkv + (static_cast<int64_t>(b) * p.L + j * 128) * p.ld + h * AT_HD;
+          const int rows_valid = min(128, p.L - j * 128);
+          write_tile(pt_sm, gk + p.v_off, rows_valid);
+          write_tile(ds_sm, gk + p.k_off, rows_valid);
+        }
+        sm_sync();
+      }
+      // ---- item epilogue: dQ chunks (TMEM lane = query index inside the chunk)
+      mbar_wait(&bars[BB_DQ_FULL], item_cnt & 1);
+      tc_fence_after();
+      for (int i = 0; i < n_qc; ++i) {
+        const int q0 = i * AB_CW;
+        const int w = min(AB_CW, Lq - q0);
+        if (quarter * 32 < w) {
+          uint32_t a[16];
+          tmem_ld_32x16(tm_dq + i * 64 + lane_addr + part * 16, a);
+          tmem_ld_wait16(a);
+          stage16(pt_sm, a);
+        }
+        if (i == n_qc - 1) {
+          tc_fence_before();
+          mbar_arrive(&bars[BB_DQ_EMPTY]);
+        }
+        sm_sync();
+        write_tile(pt_sm, p.dqkv + (static_cast<int64_t>(b) * p.L + q0) * p.ld + p.q_off + h * AT_HD, min(w, p.L - q0));
+        sm_sync();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D[b,h,l] = sum_c dO[b,l,h*64+c] * O[b,l,h*64+c]; one warp per token row, 8 lanes per head
+__global__ void __launch_bounds__(256) attn_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int64_t ldo,
+                                                        float* __restrict__ dsum, int32_t B, int32_t H, int32_t L) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= static_cast<int64_t>(B) * L) return;
+  const int64_t b = row / L;
+  const int l = static_cast<int>(row - b * L);
+  for (int h0 = 0; h0 < H; h0 += 4) {
+    const int h = h0 + (lane >> 3);
+    float acc = 0.f;
+    if (h < H) {
+      const int64_t off = row * ldo + h * AT_HD + (lane & 7) * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + off);
+      const uint4 g = *reinterpret_cast<const uint4*>(d_o + off);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = unpack_bf16x2(aw[k]), y = unpack_bf16x2(gw[k]);
+        acc += x.x * y.x + x.y * y.y;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (h < H && (lane & 7) == 0) dsum[(b * H + h) * L + l] = acc;
+  }
+}
+
+int attention_bwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o, int64_t ldo,
+                     const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H, int32_t L, int32_t head_dim,
+                     float scale, cudaStream_t stream) {
+  const int Lq = (L + 15) & ~15;
+  if (head_dim != AT_HD || Lq > 3 * AB_CW || Lq < 16) return 0;
+  if (getenv("B200MM_ATTN_LEGACY") || getenv("B200MM_ATTN_BWD_LEGACY")) return 0;
+  const int64_t T = static_cast<int64_t>(B) * L;
+  attn_dsum_kernel<<<static_cast<int>(ceil_div(T, 8)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+                                                                        reinterpret_cast<const __nv_bfloat16*>(d_o), ldo, dsum, B, H, L);
+  int rc = check_launch("attn_dsum_kernel");
+  if (rc) return rc;
+  CUtensorMap tmQrows, tmQtile, tmDOrows;
+  rc = make_tmap_2d_bf16(&tmQrows, qkv, static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(ld), 64, Lq / 2);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmQtile, qkv, static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(ld), 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmDOrows, d_o, static_cast<uint64_t>(ldo), static_cast<uint64_t>(T), static_cast<uint64_t>(ldo), 64, Lq / 2);
+  if (rc) return rc;
+  AttnBwdTcParams p;
+  p.lse = lse; p.dsum = dsum; p.key_bias = key_bias; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.ld = ld;
+  p.B = B; p.H = H; p.L = L; p.Lq = Lq; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.scale = scale;
+  const int img_pad = (Lq * 128 + 1023) & ~1023;
+  const size_t smem = static_cast<size_t>(2) * img_pad + 8 * 16384 + static_cast<size_t>(2) * Lq * 4 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) {
+    set_last_error("attention_bwd_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return B200MM_ERR_LAUNCH;
+  }
+  const int grid = std::min(B * H, sm_count());
+  attn_bwd_tc_kernel<<<grid, AT_THREADS, smem, stream>>>(tmQrows, tmQtile, tmDOrows, p);
+  rc = check_launch("attn_bwd_tc_kernel");
   return rc ? rc : 1;
 }
 

@@ -202,7 +202,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1 KB alignment for the 128B swizzle; offset arithmetic on the __shared__ array keeps the shared address space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -339,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
+          tmem_ld_wait32(r);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 32; ++j) stage[lane * EPI_STAGE_PITCH + j] = __uint_as_float(r[j]);
@@ -385,7 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
+          tmem_ld_wait32(r);
           const int64_t nb = n0 + c * 32;
           if (nb < p.N) {
             float cm = -INFINITY;
@@ -421,7 +422,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
+          tmem_ld_wait32(r);
           if (m < p.M) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {

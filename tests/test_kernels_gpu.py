@@ -145,8 +145,12 @@ def test_embed_layernorm_bit_exact_indexing(ops):
 
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,L,H,hd,masked", [(3, 5, 2, 32, False), (2, 77, 3, 64, True), (2, 257, 2, 64, False), (2, 50, 2, 80, True),
-                                             (1, 577, 1, 80, False), (2, 86, 12, 64, True), (2, 12, 2, 16, True)])
+                                             (1, 577, 1, 80, False), (2, 86, 12, 64, True), (2, 12, 2, 16, True),
+                                             (3, 197, 2, 64, False), (2, 288, 2, 64, True), (2, 300, 1, 64, False), (1, 128, 1, 64, False),
+                                             (150, 257, 2, 64, False)])
 def test_attention_fwd_bwd(ops, B, L, H, hd, masked):
+    """hd == 64 and L <= 288 run the tcgen05 kernels (attention_tc.cu); other shapes the legacy mma.sync kernels. The last case
+    has more (batch, head) items than SMs, so the persistent kernels loop and recycle their mbarrier phases."""
     W = H * hd
     qkv = rnd(B * L, 3 * W, scale=1.0, seed=B * L + hd)
     d_o = rnd(B * L, W, seed=7)
