@@ -49,15 +49,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-
 // Order in which an item's query tiles are processed: the last tile (the short remainder, e.g. 1 row of 257) goes second, so
 // that the item ENDS with a full tile whose softmax hides the TMA latency of the next item's K / Q loads.
 __device__ __forceinline__ int tile_order(int k, int n) { return n < 3 ? k : (k == 0 ? 0 : (k == 1 ? n - 1 : k - 1)); }

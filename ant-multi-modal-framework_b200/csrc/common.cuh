@@ -60,10 +60,22 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 // activations shared by GEMM epilogues and the elementwise kernels
 // QuickGELU  x*sigmoid(1.702x)       (reference: antmmf/modules/vision/backbone/clip/model.py:222-224)
 // erf-GELU   x*0.5*(1+erf(x/sqrt2))  (reference: antmmf/modules/vision/backbone/clip/modeling_bert.py:31-37)
-__device__ __forceinline__ float act_quickgelu(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(1.702 x) = 1 / (1 + 2^(-1.702*log2(e)*x)): one FMUL, two MUFU, one FADD
+__device__ __forceinline__ float sigmoid_1702(float x) { return fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x)); }
+__device__ __forceinline__ float act_quickgelu(float x) { return x * sigmoid_1702(x); }
 __device__ __forceinline__ float dact_quickgelu(float x) {
-  float s = __fdividef(1.f, 1.f + __expf(-1.702f * x));
-  return s * (1.f + 1.702f * x * (1.f - s));
+  const float s = sigmoid_1702(x);
+  return s * fmaf(1.702f * x, 1.f - s, 1.f);
 }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dact_gelu_erf(float x) {
@@ -107,6 +119,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// variant for the single-purpose producer / issuer warps: back off between polls so that their spinning does not take issue
+// slots from the epilogue warps on the same scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -164,6 +181,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Same wait, but with the destination registers of the load as in/out operands: the compiler then cannot schedule arithmetic on
 // them above the wait (the asynchronous tcgen05.ld has not written them before it).

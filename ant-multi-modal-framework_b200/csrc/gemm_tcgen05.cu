@@ -119,61 +119,69 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
   }
 }
 
-// Epilogue of the GEMM warps with the extra operands already in registers (software-pipelined loads, see the kernel):
-// `bias8` / `ext8` are the raw bf16x8 vectors of bias[n..n+8) and of the one [M,N] side input (dact_in if set, else residual).
-__device__ __forceinline__ void epi_math_store8(float (&v)[8], int64_t m, int64_t n, const EpiParams& e, const uint4& bias8,
-                                                const uint4& ext8) {
+// Lean per-8-column epilogue for the GEMM warps: every address and flag is resolved by the caller once per tile / chunk;
+// here only arithmetic, one optional aux store and the output store remain.
+struct EpiFlags {
+  bool has_bias, has_aux, has_res, has_dact, f32, scale;
+  int act;
+};
+__device__ __forceinline__ void epi_lean8(float (&v)[8], const EpiFlags& f, float alpha, const uint4& bias8, const uint4& ext8, void* dptr,
+                                          __nv_bfloat16* auxptr) {
+  if (f.scale) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] *= e.alpha;
-  if (e.bias != nullptr) {
-    float2 f0 = unpack_bf16x2(bias8.x), f1 = unpack_bf16x2(bias8.y), f2 = unpack_bf16x2(bias8.z), f3 = unpack_bf16x2(bias8.w);
+    for (int j = 0; j < 8; ++j) v[j] *= alpha;
+  }
+  if (f.has_bias) {
+    const float2 f0 = unpack_bf16x2(bias8.x), f1 = unpack_bf16x2(bias8.y), f2 = unpack_bf16x2(bias8.z), f3 = unpack_bf16x2(bias8.w);
     v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
     v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
   }
-  if (e.aux_out != nullptr) {
+  if (f.has_aux) {
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
     o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(e.aux_out + m * e.ldd + n) = o;
+    *reinterpret_cast<uint4*>(auxptr) = o;
   }
-  float2 x0 = unpack_bf16x2(ext8.x), x1 = unpack_bf16x2(ext8.y), x2 = unpack_bf16x2(ext8.z), x3 = unpack_bf16x2(ext8.w);
-  const float x[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
-  if (e.dact_in != nullptr) {
-    if (e.act == B200MM_ACT_QUICKGELU) {
+  if (f.has_dact || f.has_res) {
+    const float2 x0 = unpack_bf16x2(ext8.x), x1 = unpack_bf16x2(ext8.y), x2 = unpack_bf16x2(ext8.z), x3 = unpack_bf16x2(ext8.w);
+    const float x[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+    if (f.has_dact) {
+      if (f.act == B200MM_ACT_QUICKGELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= dact_quickgelu(x[j]);
-    } else if (e.act == B200MM_ACT_GELU_ERF) {
+        for (int j = 0; j < 8; ++j) v[j] *= dact_quickgelu(x[j]);
+      } else if (f.act == B200MM_ACT_GELU_ERF) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= dact_gelu_erf(x[j]);
-    }
-    if (e.residual != nullptr) {  // rare combination: the residual was not prefetched
-      uint4 r = *reinterpret_cast<const uint4*>(e.residual + m * e.ldr + n);
-      float2 f0 = unpack_bf16x2(r.x), f1 = unpack_bf16x2(r.y), f2 = unpack_bf16x2(r.z), f3 = unpack_bf16x2(r.w);
-      v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
-      v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
-    }
-  } else {
-    if (e.act == B200MM_ACT_QUICKGELU) {
+        for (int j = 0; j < 8; ++j) v[j] *= dact_gelu_erf(x[j]);
+      }
+    } else {
+      if (f.act == B200MM_ACT_QUICKGELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = act_quickgelu(v[j]);
-    } else if (e.act == B200MM_ACT_GELU_ERF) {
+        for (int j = 0; j < 8; ++j) v[j] = act_quickgelu(v[j]);
+      } else if (f.act == B200MM_ACT_GELU_ERF) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
-    }
-    if (e.residual != nullptr) {
+        for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += x[j];
     }
+  } else {
+    if (f.act == B200MM_ACT_QUICKGELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_quickgelu(v[j]);
+    } else if (f.act == B200MM_ACT_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
+    }
   }
-  if (e.d_f32) {
-    float* d = reinterpret_cast<float*>(e.D) + m * e.ldd + n;
+  if (f.f32) {
+    float* d = reinterpret_cast<float*>(dptr);
     *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
   } else {
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
     o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + m * e.ldd + n) = o;
+    *reinterpret_cast<uint4*>(dptr) = o;
   }
 }
 
@@ -238,7 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord tc = decode_tile(t, p);
       const int32_t m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
       for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -270,11 +278,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(t, p);
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      mbar_wait_relaxed(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_relaxed(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
@@ -310,23 +318,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord tc = decode_tile(t, p);
       const int64_t m = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32 + lane;
       const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN + half * (BN / 2);
-      // side input of the fused epilogue (dact_in or residual): its 4x16B per lane and chunk are fetched one chunk ahead, the
-      // first chunk even before the accumulator is ready, so their HBM latency overlaps the MMA / the previous chunk's math
+      // Everything that does not depend on the chunk is resolved once per tile: flags, the 4 row pointers of this lane
+      // (row = it*8 + lane/4, 8 columns starting at (lane%4)*8) for D, aux_out and the side input (dact_in if set, else
+      // residual), and row validity. The side input is fetched one chunk ahead (the first chunk before the accumulator is
+      // even ready), so its HBM latency overlaps the MMA / the previous chunk's math.
       const int rr = lane >> 2, cg = (lane & 3) * 8;
       const int64_t m_base = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32;
-      const __nv_bfloat16* ext = nullptr;
-      int64_t ld_ext = 0;
+      EpiFlags fl{};
+      const __nv_bfloat16* extp[4] = {nullptr, nullptr, nullptr, nullptr};
+      uint8_t* dp[4] = {nullptr, nullptr, nullptr, nullptr};
+      __nv_bfloat16* auxp[4] = {nullptr, nullptr, nullptr, nullptr};  // aux_out shares D's pitch but is always bf16
+      uint32_t row_ok = 0;
       uint4 nxt[4];
+      const bool is_partial = (EPI == EPI_STD) && p.partial != nullptr;
       if constexpr (EPI == EPI_STD) {
-        if (p.partial == nullptr) {
-          ext = p.epi.dact_in != nullptr ? p.epi.dact_in : p.epi.residual;
-          ld_ext = p.epi.dact_in != nullptr ? p.epi.ld_dact : p.epi.ldr;
+        const int esz = is_partial || p.epi.d_f32 ? 4 : 2;
+        if (!is_partial) {
+          fl.has_bias = p.epi.bias != nullptr; fl.has_aux = p.epi.aux_out != nullptr; fl.has_res = p.epi.residual != nullptr;
+          fl.has_dact = p.epi.dact_in != nullptr; fl.f32 = p.epi.d_f32 != 0; fl.scale = p.epi.alpha != 1.f; fl.act = p.epi.act;
+        } else {
+          fl.f32 = true;
         }
+        const __nv_bfloat16* ext = is_partial ? nullptr : (fl.has_dact ? p.epi.dact_in : p.epi.residual);
+        const int64_t ld_ext = fl.has_dact ? p.epi.ld_dact : p.epi.ldr;
+        uint8_t* dbase = is_partial ? reinterpret_cast<uint8_t*>(p.partial + static_cast<int64_t>(tc.split) * p.M * p.N)
+                                    : reinterpret_cast<uint8_t*>(p.epi.D);
+        const int64_t ldd = is_partial ? p.N : p.epi.ldd;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          nxt[it] = make_uint4(0u, 0u, 0u, 0u);
           const int64_t mm = m_base + it * 8 + rr;
-          if (ext != nullptr && mm < p.M && n0 + cg < p.N) nxt[it] = *reinterpret_cast<const uint4*>(ext + mm * ld_ext + n0 + cg);
+          if (mm < p.M) row_ok |= 1u << it;
+          dp[it] = dbase + (mm * ldd + n0 + cg) * esz;
+          auxp[it] = fl.has_aux ? p.epi.aux_out + mm * ldd + n0 + cg : nullptr;
+          extp[it] = ext != nullptr ? ext + mm * ld_ext + n0 + cg : nullptr;
+          nxt[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (ext != nullptr && mm < p.M && n0 + cg < p.N) nxt[it] = *reinterpret_cast<const uint4*>(extp[it]);
         }
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -336,6 +362,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // TMEM gives each thread one row (32 consecutive columns). Going to HBM like that would touch 32 different lines per
         // warp instruction, so the 32x32 chunk is transposed through a warp-private smem tile: afterwards 4 lanes cover
         // 64 contiguous bytes of one row and every load/store of the fused epilogue is sector-exact.
+        const int esz = fl.f32 ? 4 : 2;
+        const bool has_ext = extp[0] != nullptr;
+        const __nv_bfloat16* biasp = fl.has_bias ? p.epi.bias + n0 + cg : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c) {
           uint32_t r[32];
@@ -345,35 +374,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) stage[lane * EPI_STAGE_PITCH + j] = __uint_as_float(r[j]);
           __syncwarp();
-          const int64_t n = n0 + c * 32 + cg;
+          const bool col_ok = n0 + c * 32 + cg < p.N;
           uint4 cur[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
-          if (ext != nullptr && c + 1 < BN / 64) {
+          if (has_ext && c + 1 < BN / 64 && n0 + (c + 1) * 32 + cg < p.N) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int64_t mm = m_base + it * 8 + rr;
-              if (mm < p.M && n + 32 < p.N) nxt[it] = *reinterpret_cast<const uint4*>(ext + mm * ld_ext + n + 32);
-            }
+            for (int it = 0; it < 4; ++it)
+              if (row_ok & (1u << it)) nxt[it] = *reinterpret_cast<const uint4*>(extp[it] + (c + 1) * 32);
           }
-          if (n < p.N) {
+          if (col_ok) {
             uint4 bias8 = make_uint4(0u, 0u, 0u, 0u);
-            if (p.partial == nullptr && p.epi.bias != nullptr) bias8 = *reinterpret_cast<const uint4*>(p.epi.bias + n);
+            if (fl.has_bias) bias8 = *reinterpret_cast<const uint4*>(biasp + c * 32);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              const int row = it * 8 + rr;
-              const int64_t mm = m_base + row;
-              if (mm < p.M) {
+              if (row_ok & (1u << it)) {
                 float v[8];
+                const float* srow = stage + (it * 8 + rr) * EPI_STAGE_PITCH + cg;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = stage[row * EPI_STAGE_PITCH + cg + j];
-                if (p.partial != nullptr) {
-                  float* d = p.partial + (static_cast<int64_t>(tc.split) * p.M + mm) * p.N + n;
-                  *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-                  *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-                  epi_math_store8(v, mm, n, p.epi, bias8, cur[it]);
-                }
+                for (int j = 0; j < 8; ++j) v[j] = srow[j];
+                epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], dp[it] + c * 32 * esz, auxp[it] + c * 32);
               }
             }
           }
@@ -557,6 +577,7 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   B200MM_REQUIRE(!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, B200MM_ERR_ALIGN, "gemm: bias alignment");
   B200MM_REQUIRE(!a->aux_out || (reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0, B200MM_ERR_ALIGN, "gemm: aux_out alignment");
   B200MM_REQUIRE(a->act >= 0 && a->act <= 2, B200MM_ERR_SHAPE, "gemm: unknown activation %d", a->act);
+  B200MM_REQUIRE(!(a->dact_in && a->residual), B200MM_ERR_SHAPE, "gemm: dact_in and residual are mutually exclusive");
 
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;

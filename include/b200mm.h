@@ -51,7 +51,7 @@ int b200mm_check_device(void);
  * Epilogue, per element, in this order (fp32):
  *   v = alpha*acc; v += bias[n] (bf16, optional); if aux_out: aux_out[m,n] = v (bf16, pre-activation);
  *   v = act(v); if dact_in: v *= act'(dact_in[m,n]) (act is then applied as derivative only, not to v);
- *   v += residual[m,n] (bf16, optional); D[m,n] = v (bf16 if d_f32 == 0 else f32)
+ *   v += residual[m,n] (bf16, optional; not together with dact_in); D[m,n] = v (bf16 if d_f32 == 0 else f32)
  * splits > 1 partitions K over `splits` CTAs per tile; partial sums go to `workspace`
  * (f32, >= b200mm_gemm_workspace_bytes) and a second kernel reduces them and applies the epilogue.
  * ------------------------------------------------------------------------------------------- */
