@@ -56,37 +56,45 @@ def _vit_block_forward(x, p, B, L, H, eps):
     g, u = ops.gemm(h2, fc_w, bias=fc_b, act=ACT_QUICKGELU, aux_out=True)
     del h2
     y = ops.gemm(g, proj_w, bias=proj_b, residual=x_mid)
-    return y, (mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u)
+    return y, (mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u), g
 
 
 class VitBlockFn(Function):
     @staticmethod
-    def forward(ctx, x, ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b, B, L, H, eps, checkpoint):
+    def forward(ctx, x, ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b, B, L, H, eps, checkpoint,
+                keep_act):
         p = (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b)
-        y, saved = _vit_block_forward(x, p, B, L, H, eps)
-        ctx.meta = (B, L, H, eps, checkpoint)
+        y, saved, g = _vit_block_forward(x, p, B, L, H, eps)
+        keep_act = bool(keep_act) and not checkpoint
+        ctx.meta = (B, L, H, eps, checkpoint, keep_act)
         if checkpoint:
             ctx.save_for_backward(x, *p)
+        elif keep_act:  # memory for time: the activated MLP hidden is kept instead of being recomputed in backward
+            ctx.save_for_backward(x, *p, *saved, g)
         else:
             ctx.save_for_backward(x, *p, *saved)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        B, L, H, eps, checkpoint = ctx.meta
+        B, L, H, eps, checkpoint, keep_act = ctx.meta
         t = ctx.saved_tensors
         x, p = t[0], t[1:13]
         (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b) = p
+        g = None
         if checkpoint:
-            _, saved = _vit_block_forward(x, p, B, L, H, eps)
+            _, saved, g = _vit_block_forward(x, p, B, L, H, eps)
         else:
-            saved = t[13:]
+            saved = t[13:22]
+            if keep_act:
+                g = t[22]
         mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u = saved
         W = x.shape[1]
         dy = dy.contiguous()
         vg = _VecGrads(x.device, [W, W, 3 * W, W, W, W, 4 * W, W])  # ln1 w,b | in_b | out_b | ln2 w,b | fc_b | proj_b
         # ---- MLP branch
-        g = ops.act_fwd(u, ACT_QUICKGELU)
+        if g is None:
+            g = ops.act_fwd(u, ACT_QUICKGELU)
         d_proj_w = _wgrad(dy, g)
         del g
         ops.rowsum_periodic(dy, vg[7])
@@ -114,7 +122,7 @@ class VitBlockFn(Function):
         dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, vg[0], vg[1], dadd=dx_mid)
         d_ln1_w, d_ln1_b, d_in_b, d_out_b, d_ln2_w, d_ln2_b, d_fc_b, d_proj_b = vg.finish()
         return (dx, d_ln1_w, d_ln1_b, d_in_w, d_in_b, d_out_w, d_out_b, d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, d_proj_w, d_proj_b,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 # ======================================================================================================================
