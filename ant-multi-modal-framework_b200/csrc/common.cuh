@@ -77,11 +77,29 @@ __device__ __forceinline__ float dact_quickgelu(float x) {
   const float s = sigmoid_1702(x);
   return s * fmaf(1.702f * x, 1.f - s, 1.f);
 }
-__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Phi(x) = 0.5*(1+erf(x/sqrt2)) through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution):
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) e^{-z^2},  t = 1/(1 + p z),  z = |x|/sqrt2  ->  e^{-z^2} = e^{-x^2/2} is also the Gaussian pdf term
+// of the derivative, so gelu and gelu' cost one ex2, one rcp and a short FMA chain instead of libm's erff.
+__device__ __forceinline__ void gauss_cdf_pdf(float x, float& cdf, float& expo) {
+  const float ax = fabsf(x);
+  expo = fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_tail = 0.5f * poly * t * expo;  // 0.5*(1 - erf(|x|/sqrt2))
+  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+}
+__device__ __forceinline__ float act_gelu_erf(float x) {
+  float cdf, expo;
+  gauss_cdf_pdf(x, cdf, expo);
+  return x * cdf;
+}
 __device__ __forceinline__ float dact_gelu_erf(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, expo;
+  gauss_cdf_pdf(x, cdf, expo);
+  return fmaf(x * 0.3989422804014327f, expo, cdf);
 }
 __device__ __forceinline__ float apply_act(int act, float x) {
   return act == B200MM_ACT_QUICKGELU ? act_quickgelu(x) : (act == B200MM_ACT_GELU_ERF ? act_gelu_erf(x) : x);
@@ -207,6 +225,63 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
                  "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
                  "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :
+               : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// thread-block clusters / CTA pairs (cta_group::2): the two CTAs of a pair issue TMA into their own smem, but all
+// completion traffic (TMA transaction bytes, accumulator-drained arrivals) goes to the barriers of the leader CTA (rank 0),
+// whose single MMA thread drives both tensor cores with one tcgen05.mma.cta_group::2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_ptr`'s offset inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* local_smem_ptr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; `bar_cluster_addr` is the leader CTA's mbarrier (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), B's N rows split across the two CTAs' smem
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once all prior tcgen05 ops have completed
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 

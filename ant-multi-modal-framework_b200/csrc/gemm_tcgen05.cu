@@ -33,6 +33,18 @@ constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int EPI_STAGE_PITCH = 33;           // fp32 words per staged row (32 columns + 1: conflict-free both ways)
 constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH * 4;  // per epilogue warp
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;  // +1024: manual 1 KB alignment
+
+// CTA-pair variant (cta_group::2): one 256 x 256 macro-tile per pair. Each CTA holds its 128 rows of A and HALF of the B
+// tile (128 of the 256 N rows); the leader's tcgen05.mma reads both halves, so per-CTA operand traffic out of shared memory
+// drops from 12 KB to 8 KB per k-step and the smaller stages allow a 6-deep ring.
+template <int CG>
+struct PairCfg {
+  static constexpr int BN_CTA = BN / CG;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
+  static constexpr int STAGE = A_STAGE_BYTES + B_BYTES;
+  static constexpr int NSTAGES = CG == 2 ? 6 : STAGES;
+  static constexpr int SMEM = NSTAGES * STAGE + EPI_WARPS * EPI_STAGE_BYTES + 1024;
+};
 constexpr uint32_t TMEM_COLS = 512;
 
 struct EpiParams {
@@ -200,9 +212,12 @@ __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p)
   return c;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using PC = PairCfg<CG>;
+  constexpr int STAGES = PC::NSTAGES;           // shadows the 1-CTA constants inside this kernel
+  constexpr int STAGE_BYTES = PC::STAGE;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -226,15 +241,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32 * CG);  // pair: both CTAs' epilogue threads report to the leader
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_cg2(&tmem_base_smem, TMEM_COLS);
+    else tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int64_t tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;  // a pair walks the macro-tile list together
 
   const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
 
@@ -242,41 +263,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
-      const int32_t m0 = tc.m_blk * BM, n0 = tc.n_blk * BN;
+      const int32_t m0 = tc.m_blk * (BM * CG) + static_cast<int32_t>(cta_rank) * BM;
+      const int32_t n0 = tc.n_blk * BN + static_cast<int32_t>(cta_rank) * PC::BN_CTA;  // this CTA's share of the B tile
       for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
         mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           const int32_t k0 = kb * BK;
-          if constexpr (!A_MN) {
-            tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
-          } else {
+          if constexpr (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
+            } else {
 #pragma unroll
-            for (int s = 0; s < BM / 64; ++s) tma_load_2d(&tmA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
-          } else {
+              for (int s = 0; s < BM / 64; ++s) tma_load_2d(&tmA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+            } else {
 #pragma unroll
-            for (int s = 0; s < BN / 64; ++s) tma_load_2d(&tmB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
+              for (int s = 0; s < BN / 64; ++s) tma_load_2d(&tmB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
+            }
+          } else {
+            // both CTAs land their bytes on the LEADER's full barrier; only the leader arms it (for the pair's total)
+            const uint32_t lead_bar = map_to_cta(&full_bar[stage], 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);
+            if constexpr (!A_MN) {
+              tma_load_2d_cg2(&tmA, lead_bar, sa, k0, m0);
+            } else {
+#pragma unroll
+              for (int s = 0; s < BM / 64; ++s) tma_load_2d_cg2(&tmA, lead_bar, sa + s * SLAB_BYTES, m0 + 64 * s, k0);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_cg2(&tmB, lead_bar, sb, k0, n0);
+            } else {
+#pragma unroll
+              for (int s = 0; s < PC::BN_CTA / 64; ++s) tma_load_2d_cg2(&tmB, lead_bar, sb + s * SLAB_BYTES, n0 + 64 * s, k0);
+            }
           }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===================== MMA issuer (leader CTA of a pair issues for both) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
       mbar_wait_relaxed(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -295,14 +335,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                         : make_smem_desc_sw128(a_base + k * 32, p.k_lbo, p.k_sbo);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, p.mn_lbo, p.mn_sbo)
                                         : make_smem_desc_sw128(b_base + k * 32, p.k_lbo, p.k_sbo);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
+          // smem stage reusable (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+      if (lane == 0) {  // accumulator complete
+        if constexpr (CG == 2) umma_commit_cg2(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
+      }
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -314,16 +360,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ew * (32 * EPI_STAGE_PITCH);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
-      const int64_t m = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32 + lane;
+      const int64_t m_cta = static_cast<int64_t>(tc.m_blk) * (BM * CG) + cta_rank * BM;  // first row of this CTA's 128
+      const int64_t m = m_cta + quarter * 32 + lane;
       const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN + half * (BN / 2);
       // Everything that does not depend on the chunk is resolved once per tile: flags, the 4 row pointers of this lane
       // (row = it*8 + lane/4, 8 columns starting at (lane%4)*8) for D, aux_out and the side input (dact_in if set, else
       // residual), and row validity. The side input is fetched one chunk ahead (the first chunk before the accumulator is
       // even ready), so its HBM latency overlaps the MMA / the previous chunk's math.
       const int rr = lane >> 2, cg = (lane & 3) * 8;
-      const int64_t m_base = static_cast<int64_t>(tc.m_blk) * BM + quarter * 32;
+      const int64_t m_base = m_cta + quarter * 32;
       EpiFlags fl{};
       const __nv_bfloat16* extp[4] = {nullptr, nullptr, nullptr, nullptr};
       uint8_t* dp[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -472,16 +519,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      if (CG == 1 || cta_rank == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[acc], 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem half
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -506,22 +556,45 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI = EPI_STD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI>;
+template <bool A_MN, bool B_MN, int EPI, int CG>
+static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI, CG>;
+  constexpr int smem = PairCfg<CG>::SMEM;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
-      set_last_error("cudaFuncSetAttribute(gemm smem=%d): %s", GEMM_SMEM_BYTES, cudaGetErrorString(e));
+      set_last_error("cudaFuncSetAttribute(gemm smem=%d): %s", smem, cudaGetErrorString(e));
       return B200MM_ERR_LAUNCH;
     }
     attr_set = true;
   }
   const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
-  const int grid = static_cast<int>(total_tiles < sm_count() ? total_tiles : sm_count());
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs
+  const int grid = static_cast<int>(total_tiles < units ? total_tiles : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (e != cudaSuccess) {
+    set_last_error("gemm_tcgen05_kernel<CG=%d> launch: %s", CG, cudaGetErrorString(e));
+    return B200MM_ERR_LAUNCH;
+  }
   return check_launch("gemm_tcgen05_kernel");
+}
+
+template <bool A_MN, bool B_MN, int EPI = EPI_STD>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  return launch_gemm_cg<A_MN, B_MN, EPI, 1>(tmA, tmB, p, stream);
 }
 
 // Merge per-tile (max, sum-exp) partials of up to two logit blocks into one log-sum-exp per row.
@@ -579,9 +652,13 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   B200MM_REQUIRE(a->act >= 0 && a->act <= 2, B200MM_ERR_SHAPE, "gemm: unknown activation %d", a->act);
   B200MM_REQUIRE(!(a->dact_in && a->residual), B200MM_ERR_SHAPE, "gemm: dact_in and residual are mutually exclusive");
 
+  // CTA-pair (cta_group::2) kernels for everything that has at least one 256-row macro-tile per pair; B200MM_GEMM_CG=1 forces
+  // the single-CTA kernels
+  static const int cg_env = getenv("B200MM_GEMM_CG") ? atoi(getenv("B200MM_GEMM_CG")) : 2;
+  const int cg = (cg_env == 2 && a->M > BM) ? 2 : 1;
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
-  p.m_tiles = static_cast<int32_t>(ceil_div(a->M, BM));
+  p.m_tiles = static_cast<int32_t>(ceil_div(a->M, BM * cg));
   p.n_tiles = static_cast<int32_t>(ceil_div(a->N, BN));
   p.kb_total = static_cast<int32_t>(ceil_div(a->K, BK));
   int32_t splits = a->splits < 1 ? 1 : a->splits;
@@ -616,14 +693,21 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   if (!a->a_mn) rc = make_tmap_2d_bf16(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
   else          rc = make_tmap_2d_bf16(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
-  if (!a->b_mn) rc = make_tmap_2d_bf16(&tmB, a->B, a->K, a->N, a->ldb, BK, BN);
+  if (!a->b_mn) rc = make_tmap_2d_bf16(&tmB, a->B, a->K, a->N, a->ldb, BK, BN / cg);  // a pair's CTAs each load half of the N rows
   else          rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
 
-  if (!a->a_mn && !a->b_mn) rc = launch_gemm<false, false>(tmA, tmB, p, stream);
-  else if (!a->a_mn && a->b_mn) rc = launch_gemm<false, true>(tmA, tmB, p, stream);
-  else if (a->a_mn && !a->b_mn) rc = launch_gemm<true, false>(tmA, tmB, p, stream);
-  else rc = launch_gemm<true, true>(tmA, tmB, p, stream);
+  if (cg == 2) {
+    if (!a->a_mn && !a->b_mn) rc = launch_gemm_cg<false, false, EPI_STD, 2>(tmA, tmB, p, stream);
+    else if (!a->a_mn && a->b_mn) rc = launch_gemm_cg<false, true, EPI_STD, 2>(tmA, tmB, p, stream);
+    else if (a->a_mn && !a->b_mn) rc = launch_gemm_cg<true, false, EPI_STD, 2>(tmA, tmB, p, stream);
+    else rc = launch_gemm_cg<true, true, EPI_STD, 2>(tmA, tmB, p, stream);
+  } else {
+    if (!a->a_mn && !a->b_mn) rc = launch_gemm<false, false>(tmA, tmB, p, stream);
+    else if (!a->a_mn && a->b_mn) rc = launch_gemm<false, true>(tmA, tmB, p, stream);
+    else if (a->a_mn && !a->b_mn) rc = launch_gemm<true, false>(tmA, tmB, p, stream);
+    else rc = launch_gemm<true, true>(tmA, tmB, p, stream);
+  }
   if (rc) return rc;
 
   if (splits > 1) {

@@ -130,3 +130,59 @@ def test_no_cpu_fallback():
 
     with pytest.raises(b200mm.B200mmError):
         b200mm.ops.gemm(torch.zeros(8, 8, dtype=BF), torch.zeros(8, 8, dtype=BF))
+
+
+def test_cross_modal_stage2_path_matches_oracle():
+    """UnivlVideoBase.prepare_cross_text / prepare_cross_visual / get_cross_output
+    (prj/base_vtp/roi_univl/univl/model/univl_video_base.py:168-271) driven through the B200 text encoder exactly as the
+    reference drives RobertBertEncoder: shared embeddings (input_ids path and inputs_embeds path with token_type 1 + [SEP]),
+    concatenated [text ; clips ; SEP] sequence, additive (1-mask)*-10000 key mask, the same encoder layers, CLS @ text_projection."""
+    from b200mm.encoders import B200RobertBertEncoder
+
+    torch.manual_seed(0)
+    Hd, heads, layers, E, B, Lt, nc = 128, 2, 2, 64, 5, 11, 4
+    enc = B200RobertBertEncoder(pretrained=False, hidden_size=Hd, intermediate_size=256, num_hidden_layers=layers, num_attention_heads=heads,
+                                vocab_size=300, max_position_embeddings=64, out_dim=E, hidden_dropout_prob=0.0,
+                                attention_probs_dropout_prob=0.0).cuda().to(BF).train()
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if n.endswith("bias") or "LayerNorm.weight" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    ids = torch.randint(1, 300, (B, Lt)).cuda()
+    ids[:, 0] = 101
+    cap_mask = torch.ones(B, Lt, dtype=torch.long).cuda()
+    cap_mask[1, 7:] = 0
+    clips = (0.5 * torch.randn(B, nc, Hd)).cuda().to(BF).requires_grad_()
+    vis_pad = torch.zeros(B, nc, dtype=torch.bool).cuda()
+    vis_pad[2, 3:] = True
+
+    # ---- the reference's call sequence on the B200 modules
+    cap_embed = enc.embeddings(input_ids=ids, token_type_ids=torch.zeros_like(ids))
+    sep = enc.embeddings.word_embeddings(torch.full((B,), 102, dtype=torch.long, device="cuda")).unsqueeze(1)
+    vis_in = torch.cat([clips, sep], 1)
+    vis_embed = enc.embeddings(inputs_embeds=vis_in, token_type_ids=torch.ones(B, nc + 1, dtype=torch.long, device="cuda"))
+    vis_mask = torch.cat([vis_pad.logical_not().long(), torch.ones(B, 1, dtype=torch.long, device="cuda")], 1)
+    embed = torch.cat([cap_embed, vis_embed], 1)
+    mask = torch.cat([cap_mask, vis_mask], 1)
+    ext = (1.0 - mask.unsqueeze(1).unsqueeze(2).float()) * -10000.0
+    seq = enc.encoder(embed, attention_mask=ext, head_mask=[None] * len(enc.encoder.layer))[0]
+    pooled = seq[:, 0, :].float() @ enc.text_projection.float()
+    pooled.square().sum().backward()
+
+    # ---- oracle (fp32, same bf16-rounded parameters)
+    sd = {k: v.detach().float().cpu().requires_grad_(torch.is_floating_point(v)) for k, v in enc.module.state_dict().items()}
+    clips_o = clips.detach().float().cpu().requires_grad_()
+    o_cap = restated.bert_embeddings(sd, "embeddings.", ids.cpu(), torch.zeros(B, Lt, dtype=torch.long))
+    o_sep = sd["embeddings.word_embeddings.weight"][torch.full((B,), 102)].unsqueeze(1)
+    o_vis = restated.bert_embeddings(sd, "embeddings.", None, torch.ones(B, nc + 1, dtype=torch.long), inputs_embeds=torch.cat([clips_o, o_sep], 1))
+    o_embed = torch.cat([o_cap, o_vis], 1)
+    o_seq = restated.bert_encoder(sd, "encoder.", o_embed, heads, mask.cpu().float())
+    o_pooled = o_seq[:, 0, :] @ enc.text_projection.detach().float().cpu()
+    o_pooled.square().sum().backward()
+    valid = mask.bool().cpu()
+    assert rel_l2(seq.float().cpu()[valid], o_seq[valid]) < 1.5e-2
+    assert rel_l2(pooled, o_pooled) < 1.5e-2
+    assert rel_l2(clips.grad, clips_o.grad) < 4e-2
+    g_word = enc.embeddings.word_embeddings.weight.grad
+    assert rel_l2(g_word, sd["embeddings.word_embeddings.weight"].grad) < 4e-2
+    assert float(g_word[0].abs().max()) == 0.0  # padding_idx
