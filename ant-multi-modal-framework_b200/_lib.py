@@ -46,9 +46,9 @@ SIGNATURES = {
     "b200mm_attention_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P]),
     "b200mm_attention_bwd": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P]),
     "b200mm_contrast_num_tiles": (c_int32, [c_int64]),
-    "b200mm_contrast_lse_partials": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P]),
+    "b200mm_contrast_lse_partials": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P]),
     "b200mm_contrast_lse_merge": (c_int32, [_P, _P, c_int32, _P, _P, c_int32, _P, c_int32, _P, _P, c_int64, _P]),
-    "b200mm_contrast_softgrad": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, _P, c_float, c_float, c_int32, _P, c_int64, _P, _P]),
+    "b200mm_contrast_softgrad": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, _P, c_float, c_float, c_int32, _P, c_int64, _P, _P]),
     "b200mm_act_fwd": (c_int32, [_P, _P, c_int64, c_int32, _P]),
     "b200mm_rowsum_periodic": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P]),
     "b200mm_scatter_add_rows": (c_int32, [_P, _I64P, _P, c_int64, c_int32, c_int64, c_int64, _P]),
@@ -56,6 +56,8 @@ SIGNATURES = {
     "b200mm_rownorm_fwd": (c_int32, [_P, _P, _P, c_int64, c_int32, c_float, _P]),
     "b200mm_rownorm_bwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P]),
     "b200mm_im2row": (c_int32, [_P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, _P]),
+    "b200mm_rowdot": (c_int32, [_P, _P, _P, c_int64, c_int32, c_float, _P]),
+    "b200mm_ema_update": (c_int32, [_P, _P, c_int32, c_int64, c_float, _P]),
 }
 
 _lib = None

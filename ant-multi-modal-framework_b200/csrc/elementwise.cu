@@ -162,6 +162,36 @@ __global__ void __launch_bounds__(256) im2row_kernel(const __nv_bfloat16* __rest
   }
 }
 
+// out[r] = scale * <a[r,:], b[r,:]>  (MoCo positive logits: einsum("bh,bh->b"), univl_video_ret.py:292-296); one warp per row
+__global__ void __launch_bounds__(256) rowdot_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                     float* __restrict__ out, int64_t rows, int32_t W, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int c = lane * 8; c < W; c += 256) {
+    float x[8], y[8];
+    unpack8e(*reinterpret_cast<const uint4*>(a + row * W + c), x);
+    unpack8e(*reinterpret_cast<const uint4*>(b + row * W + c), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(x[j], y[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc * scale;
+}
+
+// momentum (EMA) update of a key-encoder parameter kept in fp32: pk = m*pk + (1-m)*pq  (moco_utils.py:55-69).
+// fp32 master copy on purpose: with m = 0.9999 the increment is below bf16 resolution.
+template <typename TQ>
+__global__ void __launch_bounds__(256) ema_update_kernel(float* __restrict__ pk, const TQ* __restrict__ pq, int64_t n, float m) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    float q;
+    if constexpr (sizeof(TQ) == 2) q = __bfloat162float(pq[i]);
+    else q = pq[i];
+    pk[i] = fmaf(pk[i], m, q * (1.f - m));
+  }
+}
+
 static inline int grid_for(int64_t work_items, int threads = 256, int waves = 8) {
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(work_items, threads), static_cast<int64_t>(sm_count()) * waves)));
 }
@@ -238,4 +268,23 @@ extern "C" int b200mm_im2row(const void* img, void* out, int64_t B, int32_t C, i
   im2row_kernel<<<grid_for(B * L * Kp), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(img),
                                                                  reinterpret_cast<__nv_bfloat16*>(out), B, C, H, Wd, p, Kp);
   return check_launch("im2row_kernel");
+}
+
+extern "C" int b200mm_rowdot(const void* a, const void* b, float* out, int64_t rows, int32_t W, float scale, void* stream) {
+  B200MM_REQUIRE(rows >= 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "rowdot: rows=%lld W=%d", (long long)rows, W);
+  if (rows == 0) return B200MM_OK;
+  B200MM_REQUIRE(ALIGNED16(a) && ALIGNED16(b), B200MM_ERR_ALIGN, "rowdot: pointers must be 16B aligned");
+  rowdot_kernel<<<static_cast<int>(ceil_div(rows, 8)), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                                                 reinterpret_cast<const __nv_bfloat16*>(b), out, rows, W, scale);
+  return check_launch("rowdot_kernel");
+}
+
+extern "C" int b200mm_ema_update(float* pk, const void* pq, int32_t pq_is_bf16, int64_t n, float m, void* stream) {
+  if (n <= 0) return B200MM_OK;
+  B200MM_REQUIRE(pk && pq, B200MM_ERR_SHAPE, "ema_update: null pointer");
+  if (pq_is_bf16)
+    ema_update_kernel<<<grid_for(n), 256, 0, STREAM(stream)>>>(pk, reinterpret_cast<const __nv_bfloat16*>(pq), n, m);
+  else
+    ema_update_kernel<<<grid_for(n), 256, 0, STREAM(stream)>>>(pk, reinterpret_cast<const float*>(pq), n, m);
+  return check_launch("ema_update_kernel");
 }

@@ -28,7 +28,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SLAB_BYTES = 64 * BK * 2;  // MN-major operands arrive as 64(mn) x 64(k) slabs of 8 KB
-constexpr int EPI_WARPS = 8;                  // warp e: TMEM lane quarter e % 4, column half e / 4
+constexpr int EPI_WARPS = 12;                 // warp e: TMEM lane quarter e % 4; 32-column chunks c with c % 3 == e / 4
+constexpr int EPI_PARTS = EPI_WARPS / 4;      // (3 warps per scheduler: the epilogue is latency-bound, not issue-bound)
+constexpr int EPI_CHUNKS = BN / 32;
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int EPI_STAGE_PITCH = 33;           // fp32 words per staged row (32 columns + 1: conflict-free both ways)
 constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH * 4;  // per epilogue warp
@@ -42,7 +44,7 @@ struct PairCfg {
   static constexpr int BN_CTA = BN / CG;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE = A_STAGE_BYTES + B_BYTES;
-  static constexpr int NSTAGES = CG == 2 ? 6 : STAGES;
+  static constexpr int NSTAGES = CG == 2 ? 5 : 3;  // what fits next to the 12 epilogue staging tiles (CG == 1 only serves M <= 128)
   static constexpr int SMEM = NSTAGES * STAGE + EPI_WARPS * EPI_STAGE_BYTES + 1024;
 };
 constexpr uint32_t TMEM_COLS = 512;
@@ -356,7 +358,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== epilogue =====================
     const int ew = warp - 4;
     const int quarter = ew & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-    const int half = ew >> 2;    // columns [128*half, 128*half+128) of the 256-wide accumulator
+    const int cpart = ew >> 2;   // this warp's 32-column chunks: c = cpart, cpart + 3, (cpart + 6)
     float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + ew * (32 * EPI_STAGE_PITCH);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -364,7 +366,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord tc = decode_tile(t, p);
       const int64_t m_cta = static_cast<int64_t>(tc.m_blk) * (BM * CG) + cta_rank * BM;  // first row of this CTA's 128
       const int64_t m = m_cta + quarter * 32 + lane;
-      const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN + half * (BN / 2);
+      const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN;
       // Everything that does not depend on the chunk is resolved once per tile: flags, the 4 row pointers of this lane
       // (row = it*8 + lane/4, 8 columns starting at (lane%4)*8) for D, aux_out and the side input (dact_in if set, else
       // residual), and row validity. The side input is fetched one chunk ahead (the first chunk before the accumulator is
@@ -372,9 +374,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int rr = lane >> 2, cg = (lane & 3) * 8;
       const int64_t m_base = m_cta + quarter * 32;
       EpiFlags fl{};
-      const __nv_bfloat16* extp[4] = {nullptr, nullptr, nullptr, nullptr};
-      uint8_t* dp[4] = {nullptr, nullptr, nullptr, nullptr};
-      __nv_bfloat16* auxp[4] = {nullptr, nullptr, nullptr, nullptr};  // aux_out shares D's pitch but is always bf16
+      // row pointers of this lane for it = 0 and the byte / element step to the next `it` (8 rows further down)
+      const __nv_bfloat16* ext0 = nullptr;
+      uint8_t* d0 = nullptr;
+      __nv_bfloat16* aux0 = nullptr;  // aux_out shares D's pitch but is always bf16
+      int64_t d_step = 0, ext_step = 0, aux_step = 0;
       uint32_t row_ok = 0;
       uint4 nxt[4];
       const bool is_partial = (EPI == EPI_STD) && p.partial != nullptr;
@@ -391,29 +395,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* dbase = is_partial ? reinterpret_cast<uint8_t*>(p.partial + static_cast<int64_t>(tc.split) * p.M * p.N)
                                     : reinterpret_cast<uint8_t*>(p.epi.D);
         const int64_t ldd = is_partial ? p.N : p.epi.ldd;
+        const int64_t mm0 = m_base + rr;
+        d0 = dbase + (mm0 * ldd + n0 + cg) * esz;
+        d_step = 8 * ldd * esz;
+        if (fl.has_aux) { aux0 = p.epi.aux_out + mm0 * ldd + n0 + cg; aux_step = 8 * ldd; }
+        if (ext != nullptr) { ext0 = ext + mm0 * ld_ext + n0 + cg; ext_step = 8 * ld_ext; }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int64_t mm = m_base + it * 8 + rr;
+          const int64_t mm = mm0 + it * 8;
           if (mm < p.M) row_ok |= 1u << it;
-          dp[it] = dbase + (mm * ldd + n0 + cg) * esz;
-          auxp[it] = fl.has_aux ? p.epi.aux_out + mm * ldd + n0 + cg : nullptr;
-          extp[it] = ext != nullptr ? ext + mm * ld_ext + n0 + cg : nullptr;
           nxt[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (ext != nullptr && mm < p.M && n0 + cg < p.N) nxt[it] = *reinterpret_cast<const uint4*>(extp[it]);
+          if (ext != nullptr && mm < p.M && n0 + cpart * 32 + cg < p.N) nxt[it] = *reinterpret_cast<const uint4*>(ext0 + it * ext_step + cpart * 32);
         }
+      }
+      // bias of this lane's 8 columns: like the side input it is fetched one chunk ahead (first chunk: before the accumulator is ready)
+      uint4 nxt_bias = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (EPI == EPI_STD) {
+        if (fl.has_bias && n0 + cpart * 32 + cg < p.N) nxt_bias = *reinterpret_cast<const uint4*>(p.epi.bias + n0 + cpart * 32 + cg);
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if constexpr (EPI == EPI_STD) {
         // TMEM gives each thread one row (32 consecutive columns). Going to HBM like that would touch 32 different lines per
         // warp instruction, so the 32x32 chunk is transposed through a warp-private smem tile: afterwards 4 lanes cover
         // 64 contiguous bytes of one row and every load/store of the fused epilogue is sector-exact.
         const int esz = fl.f32 ? 4 : 2;
-        const bool has_ext = extp[0] != nullptr;
-        const __nv_bfloat16* biasp = fl.has_bias ? p.epi.bias + n0 + cg : nullptr;
+        const bool has_ext = ext0 != nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait32(r);
@@ -425,14 +435,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint4 cur[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
-          if (has_ext && c + 1 < BN / 64 && n0 + (c + 1) * 32 + cg < p.N) {
+          if (has_ext && c + EPI_PARTS < EPI_CHUNKS && n0 + (c + EPI_PARTS) * 32 + cg < p.N) {
 #pragma unroll
             for (int it = 0; it < 4; ++it)
-              if (row_ok & (1u << it)) nxt[it] = *reinterpret_cast<const uint4*>(extp[it] + (c + 1) * 32);
+              if (row_ok & (1u << it)) nxt[it] = *reinterpret_cast<const uint4*>(ext0 + it * ext_step + (c + EPI_PARTS) * 32);
           }
+          const uint4 bias8 = nxt_bias;
+          if (fl.has_bias && c + EPI_PARTS < EPI_CHUNKS && n0 + (c + EPI_PARTS) * 32 + cg < p.N)
+            nxt_bias = *reinterpret_cast<const uint4*>(p.epi.bias + n0 + (c + EPI_PARTS) * 32 + cg);
           if (col_ok) {
-            uint4 bias8 = make_uint4(0u, 0u, 0u, 0u);
-            if (fl.has_bias) bias8 = *reinterpret_cast<const uint4*>(biasp + c * 32);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               if (row_ok & (1u << it)) {
@@ -440,7 +451,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const float* srow = stage + (it * 8 + rr) * EPI_STAGE_PITCH + cg;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = srow[j];
-                epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], dp[it] + c * 32 * esz, auxp[it] + c * 32);
+                epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], d0 + it * d_step + c * 32 * esz, aux0 + it * aux_step + c * 32);
               }
             }
           }
@@ -450,7 +461,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float mx = -INFINITY, sm = 0.f;
         const int64_t dcol = m + p.con.diag_off;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait32(r);
@@ -477,8 +488,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (m < p.M) {
-          p.con.part_max[m * (2 * p.n_tiles) + 2 * tc.n_blk + half] = mx;
-          p.con.part_sum[m * (2 * p.n_tiles) + 2 * tc.n_blk + half] = sm;
+          p.con.part_max[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = mx;
+          p.con.part_sum[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = sm;
         }
       } else {
         const float lse = m < p.M ? p.con.row_lse[m] : 0.f;
@@ -486,7 +497,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float ds_acc = 0.f;
         __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.epi.D) + m * p.epi.ldd;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait32(r);
@@ -600,6 +611,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // Merge per-tile (max, sum-exp) partials of up to two logit blocks into one log-sum-exp per row.
 //   lse[m] = log( sum_t sumA[m,t] e^{maxA[m,t]} (+ sum_t sumB[m,t] e^{maxB[m,t]}) (- e^{diag[m]} if sub_diag) )
 //   loss_sum += sum_m (lse[m] - diag[m])            (fp32 atomic; caller zero-fills)
+// sub_diag < 0 ADDS e^{diag[m]} instead (MoCo: LSE over the positive logit and the queue negatives, moco_utils.py:71-81).
 // sub_diag implements MIL-NCE's union {video_j·all texts} ∪ {text_j·videos k != j}, where the positive logit would
 // otherwise be counted twice (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197).
 __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ maxA, const float* __restrict__ sumA, int32_t tA,
@@ -616,7 +628,13 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
     for (int t = 0; t < tA; ++t) sm += sumA[m * tA + t] * __expf(maxA[m * tA + t] - mx);
     for (int t = 0; t < tB; ++t) sm += sumB[m * tB + t] * __expf(maxB[m * tB + t] - mx);
     const float d = diag[m];
-    if (sub_diag) sm -= __expf(d - mx);
+    if (sub_diag > 0) {
+      sm -= __expf(d - mx);
+    } else if (sub_diag < 0) {  // the extra logit d joins the log-sum-exp (MoCo: positive + queue negatives)
+      const float nm = fmaxf(mx, d);
+      sm = sm * __expf(mx - nm) + __expf(d - nm);
+      mx = nm;
+    }
     const float l = mx + __logf(sm);
     lse[m] = l;
     term = l - d;
@@ -724,7 +742,7 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
 // TMEM and consumed in the epilogue; the [M, N] logit matrix is never written to HBM in forward.
 // ---------------------------------------------------------------------------------------------------------------
 static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const void* a, int64_t lda, const void* b, int64_t ldb,
-                       int64_t M, int64_t N, int64_t K, float alpha) {
+                       int32_t b_mn, int64_t M, int64_t N, int64_t K, float alpha) {
   B200MM_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), B200MM_ERR_SHAPE,
                  "contrast: M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   B200MM_REQUIRE(a && b, B200MM_ERR_SHAPE, "contrast: null operand");
@@ -740,20 +758,22 @@ static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const 
   p.epi.alpha = alpha;
   int rc = make_tmap_2d_bf16(&tmA, a, K, M, lda, BK, BM);
   if (rc) return rc;
-  return make_tmap_2d_bf16(&tmB, b, K, N, ldb, BK, BN);
+  if (!b_mn) return make_tmap_2d_bf16(&tmB, b, K, N, ldb, BK, BN);
+  return make_tmap_2d_bf16(&tmB, b, N, K, ldb, 64, BK);  // b stored [K, N] row-major (e.g. the MoCo queue [dim, K_queue])
 }
 
-extern "C" int32_t b200mm_contrast_num_tiles(int64_t N) { return static_cast<int32_t>(2 * ceil_div(N, BN)); }  // one partial per 128 columns
+extern "C" int32_t b200mm_contrast_num_tiles(int64_t N) { return static_cast<int32_t>(EPI_PARTS * ceil_div(N, BN)); }  // partials per row
 
-extern "C" int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                                            float alpha, int64_t diag_off, float* part_max, float* part_sum, float* diag,
+extern "C" int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N,
+                                            int64_t K, float alpha, int64_t diag_off, float* part_max, float* part_sum, float* diag,
                                             void* stream) {
   GemmParams p;
   CUtensorMap tmA, tmB;
-  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, M, N, K, alpha);
+  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, b_mn, M, N, K, alpha);
   if (rc) return rc;
   B200MM_REQUIRE(part_max && part_sum && diag, B200MM_ERR_SHAPE, "contrast_lse_partials: null output");
   p.con.part_max = part_max; p.con.part_sum = part_sum; p.con.diag = diag; p.con.diag_off = diag_off;
+  if (b_mn) return launch_gemm<false, true, EPI_LSE>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<false, false, EPI_LSE>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -767,17 +787,18 @@ extern "C" int b200mm_contrast_lse_merge(const float* maxA, const float* sumA, i
   return check_launch("lse_merge_kernel");
 }
 
-extern "C" int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K,
+extern "C" int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
                                         int64_t n_valid, float alpha, int64_t diag_off, const float* row_lse, float coef,
                                         float diag_sub, int32_t diag_zero, void* G, int64_t ldg, float* dscale, void* stream) {
   GemmParams p;
   CUtensorMap tmA, tmB;
-  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, M, N, K, alpha);
+  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, b_mn, M, N, K, alpha);
   if (rc) return rc;
   B200MM_REQUIRE(row_lse && G && N % 8 == 0 && ldg % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, B200MM_ERR_ALIGN,
                  "contrast_softgrad: G must be 16B aligned, N and ldg multiples of 8");
   p.epi.D = G; p.epi.ldd = ldg;
   p.con.row_lse = row_lse; p.con.coef = coef; p.con.diag_sub = diag_sub; p.con.diag_zero = diag_zero;
   p.con.diag_off = diag_off; p.con.dscale = dscale; p.con.n_valid = n_valid;
+  if (b_mn) return launch_gemm<false, true, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<false, false, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -288,18 +288,22 @@ def im2row(img, p, Kp):
     return out
 
 
-def contrast_lse_partials(a, b, alpha, diag_off):
-    """Per-row (max, sum-exp) partials of z = alpha * a·b^T over 256-column tiles + the diagonal logit."""
+NO_DIAG = -(1 << 40)  # diag_off that never matches a column: "this block has no positive column"
+
+
+def contrast_lse_partials(a, b, alpha, diag_off, b_mn=False):
+    """Per-row (max, sum-exp) partials of z = alpha * a·b^T over 256-column tiles + the diagonal logit.
+    b: [N, K] rows, or with b_mn=True stored [K, N] (the MoCo queue layout [dim, K_queue])."""
     lib = _lib.load()
     lda = _row_major_2d(a, "a")
     ldb = _row_major_2d(b, "b")
     M, K = a.shape
-    N = b.shape[0]
+    N = b.shape[1] if b_mn else b.shape[0]
     nt = lib.b200mm_contrast_num_tiles(N)
     pmax = torch.empty((M, nt), device=a.device, dtype=torch.float32)
     psum = torch.empty_like(pmax)
     diag = torch.zeros(M, device=a.device, dtype=torch.float32)
-    _lib.check(lib.b200mm_contrast_lse_partials(_ptr(a), lda, _ptr(b), ldb, M, N, K, alpha, diag_off, _ptr(pmax), _ptr(psum), _ptr(diag),
+    _lib.check(lib.b200mm_contrast_lse_partials(_ptr(a), lda, _ptr(b), ldb, int(b_mn), M, N, K, alpha, diag_off, _ptr(pmax), _ptr(psum), _ptr(diag),
                                                 _stream()), "b200mm_contrast_lse_partials")
     _count(1)
     return pmax, psum, diag
@@ -318,16 +322,39 @@ def contrast_lse_merge(partsA, partsB, diag, sub_diag, loss_sum):
     return lse
 
 
-def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, diag_zero, dscale):
+def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, diag_zero, dscale, b_mn=False):
     """G = alpha*coef*(exp(z - row_lse) - diag_sub*[diag]) as bf16 [M, N]; dscale (f32 scalar tensor or None) += sum dL/dz * z.
     b may carry zero padding rows up to a multiple of 8; columns >= n_valid are zeroed."""
     lib = _lib.load()
     lda = _row_major_2d(a, "a")
     ldb = _row_major_2d(b, "b")
     M, K = a.shape
-    N = b.shape[0]
+    N = b.shape[1] if b_mn else b.shape[0]
     G = torch.empty((M, N), device=a.device, dtype=BF16)
-    _lib.check(lib.b200mm_contrast_softgrad(_ptr(a), lda, _ptr(b), ldb, M, N, K, n_valid, alpha, diag_off, _ptr(row_lse), coef, diag_sub,
+    _lib.check(lib.b200mm_contrast_softgrad(_ptr(a), lda, _ptr(b), ldb, int(b_mn), M, N, K, n_valid, alpha, diag_off, _ptr(row_lse), coef, diag_sub,
                                             int(diag_zero), _ptr(G), N, _ptr(dscale), _stream()), "b200mm_contrast_softgrad")
     _count(1)
     return G
+
+
+def rowdot(a, b, scale=1.0):
+    """out[r] = scale * <a[r], b[r]> (f32)."""
+    lib = _lib.load()
+    _req(a, "a", BF16, 2)
+    _req(b, "b", BF16, 2)
+    out = torch.empty(a.shape[0], device=a.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_rowdot(_ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(out), a.shape[0], a.shape[1], scale, _stream()), "b200mm_rowdot")
+    _count(1)
+    return out
+
+
+def ema_update(pk32, pq, m):
+    """pk32 (f32, in place) = m * pk32 + (1 - m) * pq (bf16 or f32)."""
+    lib = _lib.load()
+    _req(pk32, "pk", torch.float32)
+    if not (pq.is_cuda and pq.dtype in (BF16, torch.float32)) or pq.numel() != pk32.numel():
+        raise _lib.B200mmError("b200mm.ema_update: pq must be a CUDA bf16/f32 tensor of the same size")
+    if not (pk32.is_contiguous() and pq.is_contiguous()):
+        raise _lib.B200mmError("b200mm.ema_update: tensors must be contiguous")
+    _lib.check(lib.b200mm_ema_update(_ptr(pk32), _ptr(pq), int(pq.dtype == BF16), pk32.numel(), m, _stream()), "b200mm_ema_update")
+    _count(1)

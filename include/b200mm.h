@@ -121,20 +121,23 @@ int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_o
  * Contrastive similarity + log-softmax (tcgen05 GEMM with reduction epilogues).  z[m,n] = alpha * <a_m, b_n>.
  * Replaces  logit_scale.exp() * I @ T.t()  + cross-entropy (clip/cn_model.py:221-223, dmae_utils.py:528-537),
  * get_l1_simi_matrix + get_mil_nce_loss (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-226).
- * a: bf16 [M, K] (this rank's rows), b: bf16 [N, K] (all gathered rows); the positive of row m is column m + diag_off.
+ * a: bf16 [M, K] (this rank's rows), b: bf16 [N, K] (all gathered rows; b_mn = 1: stored [K, N] like the MoCo queue
+ * [dim, K_queue], moco_utils.py:39-52); the positive of row m is column m + diag_off (out of range = no positive column).
  *   lse_partials: per row and 256-column tile the (max, sum exp) pair, and the diagonal logit   (forward, nothing [M,N] written)
- *   lse_merge   : partials of one or two blocks -> lse[m]; loss_sum += sum_m (lse[m] - diag[m])
+ *   lse_merge   : partials of one or two blocks -> lse[m]; loss_sum += sum_m (lse[m] - diag[m]); sub_diag > 0 removes e^diag
+ *                 from the sum (MIL-NCE double-counted positive), sub_diag < 0 adds it (MoCo positive logit)
  *   softgrad    : G[m,n] = alpha * coef * (exp(z - row_lse[m]) - diag_sub*[n == m+diag_off]) as bf16 (dL/d<a_m,b_n>),
  *                 dscale += sum dL/dz * z (gradient w.r.t. log-temperature); feed G to b200mm_gemm_bf16 for dA, dB.
  *                 N (a multiple of 8) may include zero padding rows of b: columns >= n_valid get G = 0.
  * ------------------------------------------------------------------------------------------- */
 int32_t b200mm_contrast_num_tiles(int64_t N);
-int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K, float alpha,
-                                 int64_t diag_off, float* part_max, float* part_sum, float* diag, void* stream);
+int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
+                                 float alpha, int64_t diag_off, float* part_max, float* part_sum, float* diag, void* stream);
 int b200mm_contrast_lse_merge(const float* maxA, const float* sumA, int32_t tilesA, const float* maxB, const float* sumB,
                               int32_t tilesB, const float* diag, int32_t sub_diag, float* lse, float* loss_sum, int64_t M,
                               void* stream);
-int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int64_t N, int64_t K, int64_t n_valid,
+int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
+                             int64_t n_valid,
                              float alpha, int64_t diag_off, const float* row_lse, float coef, float diag_sub, int32_t diag_zero,
                              void* G, int64_t ldg, float* dscale, void* stream);
 
@@ -154,6 +157,10 @@ int b200mm_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* 
 /* y = x / max(||x||, eps) per row (cn_model.py:217-218; F.normalize in univl_video_base.py:114,158) and its backward (dy f32) */
 int b200mm_rownorm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int32_t W, float eps, void* stream);
 int b200mm_rownorm_bwd(const float* dy, const void* x, const float* inv_norm, void* dx, int64_t rows, int32_t W, void* stream);
+/* out[r] = scale * <a[r,:], b[r,:]> (f32): MoCo positive logits, einsum("bh,bh->b") in univl_video_ret.py:292-296 */
+int b200mm_rowdot(const void* a, const void* b, float* out, int64_t rows, int32_t W, float scale, void* stream);
+/* momentum update of a key-encoder parameter, pk (f32) = m*pk + (1-m)*pq (pq bf16 or f32): moco_utils.py:55-69 */
+int b200mm_ema_update(float* pk, const void* pq, int32_t pq_is_bf16, int64_t n, float m, void* stream);
 /* ViT stem patch extraction for conv1 (kernel == stride == p, no bias; clip/model.py:289-295,310-312):
  * img bf16 [B, C, H, W] -> out bf16 [B*(Np+1), Kp]; row b*(Np+1) (class-token slot) and columns >= C*p*p are zero. */
 int b200mm_im2row(const void* img, void* out, int64_t B, int32_t C, int32_t H, int32_t W, int32_t p, int32_t Kp, void* stream);

@@ -186,3 +186,49 @@ def test_cross_modal_stage2_path_matches_oracle():
     g_word = enc.embeddings.word_embeddings.weight.grad
     assert rel_l2(g_word, sd["embeddings.word_embeddings.weight"].grad) < 4e-2
     assert float(g_word[0].abs().max()) == 0.0  # padding_idx
+
+
+def test_moco_queue_loss_ema_and_enqueue():
+    """MocoUtils.moco_loss / momentum_update_key_encoder / dequeue_and_enqueue
+    (prj/base_vtp/roi_univl/univl/model/moco_utils.py:55-108) on the fused kernels vs the oracle (restated.moco_nce, itself pinned to the
+    reference's known answer in tests/golden/losses.pt)."""
+    import torch.nn.functional as F
+
+    from b200mm.moco import B200MocoUtils, moco_nce
+
+    torch.manual_seed(0)
+    N, E, K, T = 37, 64, 1024, 0.05
+    q = F.normalize(torch.randn(N, E), dim=-1).to(BF)
+    kp = F.normalize(q.float() + 0.5 * torch.randn(N, E), dim=-1).to(BF)
+    queue = F.normalize(torch.randn(E, K), dim=0).to(BF)
+    qf = q.float().requires_grad_()
+    pos = (qf * kp.float()).sum(-1, keepdim=True)
+    neg = qf @ queue.float()
+    ref = restated.moco_nce(pos, neg, T)
+    ref.backward()
+    qc = q.cuda().requires_grad_()
+    loss = moco_nce(qc, kp.cuda(), queue.cuda(), T)
+    assert abs(float(loss) - float(ref)) < 2e-4 * max(1.0, abs(float(ref))), (float(loss), float(ref))
+    loss.backward()
+    assert rel_l2(qc.grad, qf.grad) < 1e-2, rel_l2(qc.grad, qf.grad)
+
+    # module: same buffer names / shapes as the reference, EMA of the key encoder, ring-buffer enqueue
+    enc = torch.nn.Linear(16, 16).cuda().to(BF)
+    mu = B200MocoUtils(dict(hidden_size=E, K=K, M=0.99, T=T), txt_encoder=enc).cuda()
+    assert set(dict(mu.named_buffers())) == {"txt_queue", "txt_queue_ptr"} and mu.txt_queue.shape == (E, K)
+    w_k0 = mu.txt_encoder_k.weight.detach().clone()
+    with torch.no_grad():
+        enc.weight.add_(1.0)
+    mu.momentum_update_key_encoder()
+    expect = w_k0 * 0.99 + enc.weight.float() * 0.01
+    torch.testing.assert_close(mu.txt_encoder_k.weight, expect, rtol=1e-6, atol=1e-6)
+    keys = F.normalize(torch.randn(24, E), dim=-1).cuda().to(BF)
+    l0 = mu.moco_loss_fused(qc.detach(), kp.cuda(), "txt")
+    mu.dequeue_and_enqueue(None, keys)
+    assert int(mu.txt_queue_ptr) == 24
+    torch.testing.assert_close(mu.txt_queue[:, :24], keys.float().t())
+    l1 = mu.moco_loss_fused(qc.detach(), kp.cuda(), "txt")
+    negs = qc.detach().float() @ mu.txt_queue.to(BF).float()
+    pos_c = (qc.detach().float() * kp.cuda().float()).sum(-1, keepdim=True)
+    assert abs(float(l1) - float(restated.moco_nce(pos_c.cpu(), negs.cpu(), T))) < 2e-4 * max(1.0, float(l1))
+    assert float(l0) != float(l1)
