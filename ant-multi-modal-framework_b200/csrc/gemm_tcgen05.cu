@@ -18,6 +18,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace b200mm {
 
 constexpr int BM = 128;
@@ -133,6 +135,11 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
   }
 }
 
+// compile-time flavour encoding: bit0 bias, bit1 aux_out, bit2 residual, bit3 dact, bit4 f32 out, bit5 alpha != 1, bits 6-7 act
+__host__ __device__ constexpr int flavor_bits(bool bias, bool aux, bool res, bool dact, bool f32, bool scale, int act) {
+  return (bias ? 1 : 0) | (aux ? 2 : 0) | (res ? 4 : 0) | (dact ? 8 : 0) | (f32 ? 16 : 0) | (scale ? 32 : 0) | (act << 6);
+}
+
 // Lean per-8-column epilogue for the GEMM warps: every address and flag is resolved by the caller once per tile / chunk;
 // here only arithmetic, one optional aux store and the output store remain.
 struct EpiFlags {
@@ -214,7 +221,9 @@ __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p)
   return c;
 }
 
-template <bool A_MN, bool B_MN, int EPI, int CG>
+// FL >= 0 bakes the epilogue flags (see flavor_bits) into the kernel so that the per-element code has no flag branches;
+// FL == -1 keeps them as runtime values (any combination, edge flavours).
+template <bool A_MN, bool B_MN, int EPI, int CG, int FL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using PC = PairCfg<CG>;
@@ -390,6 +399,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
           fl.f32 = true;
         }
+        if constexpr (FL >= 0) {  // the host guarantees that the runtime arguments match the baked-in flavour
+          fl.has_bias = (FL & 1) != 0; fl.has_aux = (FL & 2) != 0; fl.has_res = (FL & 4) != 0; fl.has_dact = (FL & 8) != 0;
+          fl.f32 = (FL & 16) != 0; fl.scale = (FL & 32) != 0; fl.act = (FL >> 6) & 3;
+        }
         const __nv_bfloat16* ext = is_partial ? nullptr : (fl.has_dact ? p.epi.dact_in : p.epi.residual);
         const int64_t ld_ext = fl.has_dact ? p.epi.ld_dact : p.epi.ldr;
         uint8_t* dbase = is_partial ? reinterpret_cast<uint8_t*>(p.partial + static_cast<int64_t>(tc.split) * p.M * p.N)
@@ -422,40 +435,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // 64 contiguous bytes of one row and every load/store of the fused epilogue is sector-exact.
         const int esz = fl.f32 ? 4 : 2;
         const bool has_ext = ext0 != nullptr;
+        // interior tiles (all 128 rows and 256 columns valid) take the predicate-free instantiation of the chunk loop
+        auto chunk_loop = [&](auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll 1
-        for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait32(r);
-          __syncwarp();
+          for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait32(r);
+            __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stage[lane * EPI_STAGE_PITCH + j] = __uint_as_float(r[j]);
-          __syncwarp();
-          const bool col_ok = n0 + c * 32 + cg < p.N;
-          uint4 cur[4];
+            for (int j = 0; j < 32; ++j) stage[lane * EPI_STAGE_PITCH + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const bool col_ok = FULL || n0 + c * 32 + cg < p.N;
+            uint4 cur[4];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
-          if (has_ext && c + EPI_PARTS < EPI_CHUNKS && n0 + (c + EPI_PARTS) * 32 + cg < p.N) {
+            for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+            const bool next_ok = c + EPI_PARTS < EPI_CHUNKS && (FULL || n0 + (c + EPI_PARTS) * 32 + cg < p.N);
+            if (has_ext && next_ok) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it)
-              if (row_ok & (1u << it)) nxt[it] = *reinterpret_cast<const uint4*>(ext0 + it * ext_step + (c + EPI_PARTS) * 32);
-          }
-          const uint4 bias8 = nxt_bias;
-          if (fl.has_bias && c + EPI_PARTS < EPI_CHUNKS && n0 + (c + EPI_PARTS) * 32 + cg < p.N)
-            nxt_bias = *reinterpret_cast<const uint4*>(p.epi.bias + n0 + (c + EPI_PARTS) * 32 + cg);
-          if (col_ok) {
+              for (int it = 0; it < 4; ++it)
+                if (FULL || (row_ok & (1u << it))) nxt[it] = *reinterpret_cast<const uint4*>(ext0 + it * ext_step + (c + EPI_PARTS) * 32);
+            }
+            const uint4 bias8 = nxt_bias;
+            if (fl.has_bias && next_ok) nxt_bias = *reinterpret_cast<const uint4*>(p.epi.bias + n0 + (c + EPI_PARTS) * 32 + cg);
+            if (col_ok) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              if (row_ok & (1u << it)) {
-                float v[8];
-                const float* srow = stage + (it * 8 + rr) * EPI_STAGE_PITCH + cg;
+              for (int it = 0; it < 4; ++it) {
+                if (FULL || (row_ok & (1u << it))) {
+                  float v[8];
+                  const float* srow = stage + (it * 8 + rr) * EPI_STAGE_PITCH + cg;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = srow[j];
-                epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], d0 + it * d_step + c * 32 * esz, aux0 + it * aux_step + c * 32);
+                  for (int j = 0; j < 8; ++j) v[j] = srow[j];
+                  epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], d0 + it * d_step + c * 32 * esz, aux0 + it * aux_step + c * 32);
+                }
               }
             }
           }
-        }
+        };
+        if (m_cta + BM <= p.M && n0 + BN <= p.N) chunk_loop(std::true_type{});
+        else chunk_loop(std::false_type{});
       } else if constexpr (EPI == EPI_LSE) {
         // online (max, sum-exp) over this tile's columns of row m; the diagonal logit is captured on the way
         float mx = -INFINITY, sm = 0.f;
@@ -567,9 +586,9 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI, int CG>
+template <bool A_MN, bool B_MN, int EPI, int CG, int FL = -1>
 static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI, CG>;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI, CG, FL>;
   constexpr int smem = PairCfg<CG>::SMEM;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
@@ -716,7 +735,30 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   if (rc) return rc;
 
   if (cg == 2) {
-    if (!a->a_mn && !a->b_mn) rc = launch_gemm_cg<false, false, EPI_STD, 2>(tmA, tmB, p, stream);
+    // flavours of the training step get kernels with the epilogue flags baked in (no per-element flag branches); anything else
+    // (and split-K partial tiles) runs the runtime-flag kernel
+    const int fl = splits > 1 ? -1
+                              : flavor_bits(a->bias != nullptr, a->aux_out != nullptr, a->residual != nullptr, a->dact_in != nullptr,
+                                            a->d_f32 != 0, a->alpha != 1.f, a->act);
+    bool done = true;
+#define B200MM_TRY(AMN, BMN, ...)                                                                   \
+  else if (a->a_mn == AMN && a->b_mn == BMN && fl == flavor_bits(__VA_ARGS__))                      \
+    rc = launch_gemm_cg<AMN != 0, BMN != 0, EPI_STD, 2, flavor_bits(__VA_ARGS__)>(tmA, tmB, p, stream);
+    if (fl < 0) done = false;
+    //          bias   aux    res    dact   f32    scale  act
+    B200MM_TRY(0, 0, true, false, false, false, false, false, B200MM_ACT_NONE)       // qkv / dense projections
+    B200MM_TRY(0, 0, true, false, true, false, false, false, B200MM_ACT_NONE)        // out_proj / c_proj (+ residual)
+    B200MM_TRY(0, 0, true, true, false, false, false, false, B200MM_ACT_QUICKGELU)   // ViT c_fc
+    B200MM_TRY(0, 0, true, true, false, false, false, false, B200MM_ACT_GELU_ERF)    // BERT intermediate
+    B200MM_TRY(0, 0, false, false, false, false, false, false, B200MM_ACT_NONE)      // patch embedding
+    B200MM_TRY(0, 1, false, false, false, false, false, false, B200MM_ACT_NONE)      // plain dgrad
+    B200MM_TRY(0, 1, false, false, true, false, false, false, B200MM_ACT_NONE)       // dgrad + residual-branch gradient
+    B200MM_TRY(0, 1, false, false, false, true, false, false, B200MM_ACT_QUICKGELU)  // dgrad through QuickGELU
+    B200MM_TRY(0, 1, false, false, false, true, false, false, B200MM_ACT_GELU_ERF)   // dgrad through erf-GELU
+    else done = false;
+#undef B200MM_TRY
+    if (done) {
+    } else if (!a->a_mn && !a->b_mn) rc = launch_gemm_cg<false, false, EPI_STD, 2>(tmA, tmB, p, stream);
     else if (!a->a_mn && a->b_mn) rc = launch_gemm_cg<false, true, EPI_STD, 2>(tmA, tmB, p, stream);
     else if (a->a_mn && !a->b_mn) rc = launch_gemm_cg<true, false, EPI_STD, 2>(tmA, tmB, p, stream);
     else rc = launch_gemm_cg<true, true, EPI_STD, 2>(tmA, tmB, p, stream);
