@@ -77,9 +77,11 @@ struct ContrastParams {
   int32_t diag_zero;      // EPI_SOFTGRAD: force dL/dz = 0 on the diagonal (MIL-NCE text->video block)
   float* dscale;          // EPI_SOFTGRAD: += sum dL/dz * z  (gradient of the log-temperature), or null
   int64_t n_valid;        // EPI_SOFTGRAD: columns >= n_valid are padding (G = 0 there)
+  int32_t* rank_out;      // EPI_RANK: [M] += #{n : z[m,n] > row_lse[m], n != positive column}  (row_lse doubles as the reference logit)
+  const int32_t* gt_col;  // EPI_RANK: [M] positive column of each row, or null -> m + diag_off
 };
 
-enum { EPI_STD = 0, EPI_LSE = 1, EPI_SOFTGRAD = 2 };
+enum { EPI_STD = 0, EPI_LSE = 1, EPI_SOFTGRAD = 2, EPI_RANK = 3 };
 
 struct GemmParams {
   int64_t M, N, K;
@@ -510,6 +512,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           p.con.part_max[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = mx;
           p.con.part_sum[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = sm;
         }
+      } else if constexpr (EPI == EPI_RANK) {
+        // retrieval rank of the positive: how many logits of row m beat the reference logit (strictly), the positive itself excluded
+        const float ref = m < p.M ? p.con.row_lse[m] : INFINITY;
+        const int64_t dcol = m < p.M ? (p.con.gt_col != nullptr ? static_cast<int64_t>(p.con.gt_col[m]) : m + p.con.diag_off) : -1;
+        int cnt = 0;
+#pragma unroll 1
+        for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait32(r);
+          const int64_t nb = n0 + c * 32;
+          if (nb < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              cnt += (nb + j < p.N && nb + j != dcol && __uint_as_float(r[j]) * p.epi.alpha > ref) ? 1 : 0;
+          }
+        }
+        if (m < p.M && cnt) atomicAdd(p.con.rank_out + m, cnt);
       } else {
         const float lse = m < p.M ? p.con.row_lse[m] : 0.f;
         const int64_t dcol = m + p.con.diag_off;
@@ -843,4 +863,16 @@ extern "C" int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* 
   p.con.diag_off = diag_off; p.con.dscale = dscale; p.con.n_valid = n_valid;
   if (b_mn) return launch_gemm<false, true, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<false, false, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mm_contrast_rank(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
+                                    float alpha, int64_t diag_off, const int32_t* gt_col, const float* ref, int32_t* rank_out, void* stream) {
+  GemmParams p;
+  CUtensorMap tmA, tmB;
+  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, b_mn, M, N, K, alpha);
+  if (rc) return rc;
+  B200MM_REQUIRE(ref && rank_out, B200MM_ERR_SHAPE, "contrast_rank: null reference / output");
+  p.con.row_lse = ref; p.con.rank_out = rank_out; p.con.gt_col = gt_col; p.con.diag_off = diag_off;
+  if (b_mn) return launch_gemm<false, true, EPI_RANK>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm<false, false, EPI_RANK>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -337,6 +337,24 @@ def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, d
     return G
 
 
+def contrast_rank(a, b, alpha, ref, diag_off=0, gt_col=None, b_mn=False):
+    """rank[m] = #{n != pos(m): alpha*<a_m, b_n> > ref[m]} (int32 [M]); pos(m) = gt_col[m] (int32) or m + diag_off.
+    The [M, N] similarity only exists tile by tile in TMEM."""
+    lib = _lib.load()
+    lda = _row_major_2d(a, "a")
+    ldb = _row_major_2d(b, "b")
+    M, K = a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    _req(ref, "ref", torch.float32, 1)
+    if gt_col is not None:
+        _req(gt_col, "gt_col", torch.int32, 1)
+    rank = torch.zeros(M, device=a.device, dtype=torch.int32)
+    _lib.check(lib.b200mm_contrast_rank(_ptr(a), lda, _ptr(b), ldb, int(b_mn), M, N, K, alpha, diag_off, _ptr(gt_col), _ptr(ref), _ptr(rank),
+                                        _stream()), "b200mm_contrast_rank")
+    _count(1)
+    return rank
+
+
 def rowdot(a, b, scale=1.0):
     """out[r] = scale * <a[r], b[r]> (f32)."""
     lib = _lib.load()

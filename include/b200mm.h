@@ -140,6 +140,13 @@ int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t 
                              int64_t n_valid,
                              float alpha, int64_t diag_off, const float* row_lse, float coef, float diag_sub, int32_t diag_zero,
                              void* G, int64_t ldg, float* dscale, void* stream);
+/* Retrieval rank of the positive pair without materialising the similarity matrix — replaces the sort-based rank of
+ * _compute_retrieval_metrics (antmmf/modules/metrics/global_retrieval_recall.py:12-27) and cal_ret_metric
+ * (prj/base_vtp/roi_univl/univl/model/univl_video_pretrain.py:294-312):
+ *   rank_out[m] += #{ n != pos(m) : alpha*<a_m, b_n> > ref[m] },  pos(m) = gt_col[m] if gt_col else m + diag_off.
+ * ref[m] is the positive logit (e.g. `diag` of lse_partials, or b200mm_rowdot for arbitrary gt_col); the caller zero-fills rank_out. */
+int b200mm_contrast_rank(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
+                         float alpha, int64_t diag_off, const int32_t* gt_col, const float* ref, int32_t* rank_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small HBM-bound helpers.

@@ -117,11 +117,39 @@ def make_losses():
     print("losses.pt", {k: float(v["loss"]) for k, v in out.items()})
 
 
+def make_retrieval():
+    """Retrieval metrics of the unmodified reference on seeded embeddings (square 1:1 case and a 5-captions-per-image case)."""
+    import numpy as np
+
+    fn = ref_loader.load_retrieval_metric_functions()
+    out = {}
+    torch.manual_seed(3)
+    t = F.normalize(torch.randn(48, 16) + 0.0, dim=-1)
+    v = F.normalize(t + 0.9 * torch.randn(48, 16), dim=-1)
+    sim = (t @ v.t()).numpy()
+    out["square"] = dict(t=t, v=v, ranks=torch.from_numpy(np.asarray(fn._compute_retrieval_metrics(sim)).astype(np.int64)),
+                         recall={k: float(x) for k, x in fn._cal_recall(sim).items()})
+    # 12 images x 5 captions: texts 5i..5i+4 belong to image i
+    torch.manual_seed(4)
+    vis = F.normalize(torch.randn(12, 16), dim=-1)
+    txt = F.normalize(vis.repeat_interleave(5, 0) + 0.8 * torch.randn(60, 16), dim=-1)
+    t2v = [[i // 5] for i in range(60)]
+    v2t = [list(range(5 * i, 5 * i + 5)) for i in range(12)]
+    simm = (txt @ vis.t()).numpy()
+    out["multi_gt"] = dict(t=txt, v=vis, t2v=t2v, v2t=v2t, metrics={k: float(x) for k, x in fn._cal_sym_recall(simm, t2v, v2t).items()})
+    torch.save(out, os.path.join(OUT, "retrieval.pt"))
+    print("retrieval.pt", out["square"]["recall"], out["multi_gt"]["metrics"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--retrieval-only" in sys.argv:
+        make_retrieval()
+        sys.exit(0)
     make_cnclip("cnclip_tiny.pt", TINY, B=6, L=16, vocab_used=512)
     h80 = dict(TINY, vision_width=160, vision_head_width=80, vision_layers=1, text_hidden_size=32,
                text_num_attention_heads=2, text_num_hidden_layers=1, text_intermediate_size=64, embed_dim=16,
                image_resolution=32, vision_patch_size=16)
     make_cnclip("cnclip_tiny_h80.pt", h80, B=5, L=12, vocab_used=128)
     make_losses()
+    make_retrieval()

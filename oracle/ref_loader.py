@@ -111,6 +111,17 @@ def load_loss_functions():
     return ns
 
 
+def load_retrieval_metric_functions():
+    """Reference retrieval-metric arithmetic, unmodified (antmmf/modules/metrics/global_retrieval_recall.py:12-102)."""
+    if "ret_metric" in _loaded:
+        return _loaded["ret_metric"]
+    fns = _extract_functions("antmmf/modules/metrics/global_retrieval_recall.py", ["_compute_retrieval_metrics", "_cal_sym_recall", "_cal_recall"])
+    # the three functions call each other through module globals: they share the exec namespace, so this already resolves
+    ns = types.SimpleNamespace(**fns)
+    _loaded["ret_metric"] = ns
+    return ns
+
+
 def build_cnclip(name_or_cfg, seed=0, dropout=0.0):
     """Reference CNCLIP with the reference initialisation; ``text_projection`` (torch.empty in cn_model.py:190-192)
     gets N(0, hidden^-0.5). Dropout probabilities are overridden (parity runs use 0)."""

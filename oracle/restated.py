@@ -186,5 +186,50 @@ def l1_simi_matrix(text, video, n_clips=1):
     return torch.matmul(video.view(-1, n_clips, E), text.t()).permute(2, 0, 1)
 
 
+def retrieval_ranks(sim):
+    """0-based rank of the positive (diagonal) of every row of `sim` in descending order.
+    Restates _compute_retrieval_metrics (antmmf/modules/metrics/global_retrieval_recall.py:12-27) and cal_ret_metric
+    (prj/base_vtp/roi_univl/univl/model/univl_video_pretrain.py:294-312): the reference sorts -sim and looks up where the diagonal
+    value lands; that position is the number of strictly larger entries, and — faithfully — every entry EQUAL to the positive
+    yields one more listed position (so ties make the output longer than the number of rows)."""
+    import numpy as np
+
+    x = np.asarray(sim.detach().cpu().numpy() if isinstance(sim, torch.Tensor) else sim)
+    out = []
+    for i in range(x.shape[0]):
+        greater = int((x[i] > x[i, i]).sum())
+        equal = int((x[i] == x[i, i]).sum())
+        out.extend(range(greater, greater + equal))
+    return np.asarray(out, dtype=np.int64)
+
+
+def recall_from_ranks(ranks, eps=1e-10):
+    """mr / r@1 / r@5 / r@10 of _cal_recall (global_retrieval_recall.py:91-103): median rank is 1-based, recalls are fractions."""
+    import numpy as np
+
+    ranks = np.asarray(ranks)
+    rec = lambda k: float((ranks < k).sum() / (len(ranks) + eps))  # noqa: E731
+    return {"mr": float(np.median(ranks) + 1), "r@1": rec(1), "r@5": rec(5), "r@10": rec(10)}
+
+
+def sym_recall(sim, t2v, v2t):
+    """Both retrieval directions with several ground truths per query (_cal_sym_recall, global_retrieval_recall.py:30-88):
+    rows = texts, columns = visuals; a query's rank is the best rank among its ground-truth ids; r@k counts queries whose best
+    ground truth is inside the top k; mr = median best rank + 1. (No ties assumed: the reference's argsort order of ties is arbitrary.)"""
+    import numpy as np
+
+    x = np.asarray(sim.detach().cpu().numpy() if isinstance(sim, torch.Tensor) else sim)
+
+    def one_direction(mat, gts, tag):
+        best = np.asarray([min(int((mat[i] > mat[i, g]).sum()) for g in set(gts[i])) for i in range(mat.shape[0])])
+        r = {k: float((best < k).sum()) / mat.shape[0] for k in (1, 5, 10)}
+        return {f"{tag}-mean_recall": (r[1] + r[5] + r[10]) / 3.0, f"{tag}-r@1": r[1], f"{tag}-r@5": r[5], f"{tag}-r@10": r[10],
+                f"{tag}-mr": float(np.median(best) + 1)}
+
+    out = one_direction(x, t2v, "t2v")
+    out.update(one_direction(x.T, v2t, "v2t"))
+    return out
+
+
 def to_dtype(sd, dtype):
     return {k: (v.to(dtype) if torch.is_floating_point(v) else v) for k, v in sd.items()}

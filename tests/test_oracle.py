@@ -92,3 +92,48 @@ def test_reference_loss_functions_extract():
     assert abs(float(fn.get_mil_nce_loss(None, sim, 4, 1)) - 2.0541925) < 1e-6
     pos, neg = torch.randn(5, 1), torch.randn(5, 7)
     torch.testing.assert_close(fn.moco_loss(types.SimpleNamespace(T=0.05), pos, neg), restated.moco_nce(pos, neg, 0.05))
+
+
+def _np_sim(t, v):
+    return (t @ v.t()).numpy()
+
+
+def test_restated_retrieval_metrics_match_golden(golden_dir):
+    """oracle retrieval ranks / recalls against the vectors produced by the unmodified reference (make_golden.make_retrieval)"""
+    import numpy as np
+
+    fx = _load(golden_dir, "retrieval.pt")
+    sq = fx["square"]
+    ranks = restated.retrieval_ranks(_np_sim(sq["t"], sq["v"]))
+    assert np.array_equal(ranks, sq["ranks"].numpy())
+    got = restated.recall_from_ranks(ranks)
+    for k, v in sq["recall"].items():
+        assert abs(got[k] - v) < 1e-12, k
+    mg = fx["multi_gt"]
+    got = restated.sym_recall(_np_sim(mg["t"], mg["v"]), mg["t2v"], mg["v2t"])
+    assert set(got) == set(mg["metrics"])
+    for k, v in mg["metrics"].items():
+        assert abs(got[k] - v) < 1e-12, k
+    # ties: every entry equal to the positive is listed (the reference's np.where(sorted == diag) behaviour)
+    tie = np.array([[1.0, 1.0, 0.0], [0.5, 0.2, 0.9], [0.0, 0.0, 0.0]])
+    assert restated.retrieval_ranks(tie).tolist() == [0, 1, 2, 0, 1, 2]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_restated_retrieval_metrics_match_live_reference():
+    import numpy as np
+
+    fn = ref_loader.load_retrieval_metric_functions()
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 33):
+        x = rng.standard_normal((n, n)).astype(np.float32)
+        assert np.array_equal(restated.retrieval_ranks(x), fn._compute_retrieval_metrics(x))
+        a, b = restated.recall_from_ranks(restated.retrieval_ranks(x)), fn._cal_recall(x)
+        assert all(abs(a[k] - float(b[k])) < 1e-12 for k in b)
+    tie = np.array([[1.0, 1.0, 0.0], [0.5, 0.2, 0.9], [0.0, 0.0, 0.0]], dtype=np.float32)
+    assert np.array_equal(restated.retrieval_ranks(tie), fn._compute_retrieval_metrics(tie))
+    x = rng.standard_normal((20, 6)).astype(np.float32)
+    t2v = [[int(rng.integers(0, 6))] for _ in range(20)]
+    v2t = [sorted(set(int(i) for i in rng.integers(0, 20, size=3))) for _ in range(6)]
+    a, b = restated.sym_recall(x, t2v, v2t), fn._cal_sym_recall(x, t2v, v2t)
+    assert all(abs(a[k] - float(b[k])) < 1e-12 for k in b)
