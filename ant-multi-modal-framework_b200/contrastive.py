@@ -114,12 +114,73 @@ class _ContrastiveFn(Function):
         return da.to(BF16), db.to(BF16), d_ls, None, None
 
 
+class _MilNceClipsFn(Function):
+    """MIL-NCE with n clips per video (get_mil_nce_loss as driven by forward_stage1, univl_video_ret.py:146-197, :357-387):
+        loss = mean_j( log( n * sum_i e^{<v_{j,c}, t_i>} + sum_{k != j, c'} e^{<t_j, v_{k,c'}>} ) - <v_{j,c}, t_j> - ln n ),   c = n // 2.
+    video [B*n, E] (clips of a video adjacent), text [B, E]. Two logit blocks per rank, never materialised in forward:
+        A  = V_mid · T_all^T          [B, B_g]      rows: the middle clip of each local video
+        Bt = T_loc · V_allclips^T     [B, B_g*n]    rows: local texts, columns: every clip of every video (own video's n clips excluded)
+    """
+
+    @staticmethod
+    def forward(ctx, video, text, n, group):
+        rank, world = _world(group)
+        B, E = text.shape
+        v_mid = video.view(B, n, E)[:, n // 2].contiguous()
+        t_all, Bg = _gather_rows(text, group)
+        v_all, _ = _gather_rows(video, group)                      # [Bg*n (padded), E], clips of video k at rows k*n .. k*n+n-1
+        off = rank * B
+        pmaxA, psumA, diag = ops.contrast_lse_partials(v_mid, t_all[:Bg], 1.0, off)
+        pmaxB, psumB, _ = ops.contrast_lse_partials(text, v_all[: Bg * n], 1.0, ops.NO_DIAG)
+
+        def merge(pmax, psum):
+            m = pmax.max(dim=1).values
+            return m + torch.log((psum * torch.exp(pmax - m[:, None])).sum(dim=1))
+
+        lse_a = merge(pmaxA, psumA) + torch.log(torch.tensor(float(n), device=text.device))
+        lse_b_all = merge(pmaxB, psumB)
+        # the text's own video is not a negative: take its n clip logits out of the block-B sum
+        own = (text.float()[:, None, :] * video.view(B, n, E).float()).sum(-1)          # [B, n] (bf16 inputs, fp32 accumulate)
+        lse_b = lse_b_all + torch.log1p(-torch.exp(own - lse_b_all[:, None]).sum(dim=1).clamp(max=1.0 - 1e-7))
+        total = torch.logaddexp(lse_a, lse_b)
+        loss_sum = (total - diag).sum() - B * torch.log(torch.tensor(float(n), device=text.device))
+        ctx.save_for_backward(video, text, v_mid, t_all, v_all, total)
+        ctx.meta = (n, group, off, Bg, world)
+        return (loss_sum * (world / Bg)).reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        video, text, v_mid, t_all, v_all, total = ctx.saved_tensors
+        n, group, off, Bg, world = ctx.meta
+        B, E = text.shape
+        coef = float(gout) * world / Bg
+        ln_n = float(torch.log(torch.tensor(float(n))))
+        # dL/dA = coef * (n e^{z - total} - [i == j]);  dL/dBt = coef * e^{z - total}, zero on the own video's clips
+        GA = ops.contrast_softgrad(v_mid, t_all, Bg, 1.0, off, (total - ln_n).contiguous(), coef, 1.0, False, None)
+        GB = ops.contrast_softgrad(text, v_all, Bg * n, 1.0, ops.NO_DIAG, total, coef, 0.0, False, None)
+        rows = torch.arange(B, device=text.device)
+        GB[:, : Bg * n].view(B, Bg, n)[rows, rows + off] = 0
+        d_vmid = ops.gemm(GA, t_all, b_mn=True, out_f32=True)                       # [B, E]
+        d_text = ops.gemm(GB, v_all, b_mn=True, out_f32=True)                       # [B, E]
+        d_t_all = ops.gemm(GA, v_mid, a_mn=True, b_mn=True, out_f32=True)           # [Bg_pad, E]
+        d_v_all = ops.gemm(GB, text, a_mn=True, b_mn=True, out_f32=True)            # [(Bg*n)_pad, E]
+        d_text = d_text + _scatter_grad(d_t_all, B, group)
+        d_video = _scatter_grad(d_v_all, B * n, group).clone().view(B, n, E)
+        d_video[:, n // 2] += d_vmid
+        return d_video.view(B * n, E).to(BF16), d_text.to(BF16), None, None
+
+
 def clip_contrastive_loss(image_features, text_features, logit_scale, group=None):
     """Symmetric InfoNCE over the global batch; features [B, E] bf16 (normalised), logit_scale = log-temperature parameter."""
     d = _ContrastiveFn.apply(image_features, text_features, logit_scale, "clip", group)
     return d
 
 
-def mil_nce_loss(video_features, text_features, group=None):
-    """UnivlForVideoTextRetrieval.get_mil_nce_loss for n_clips = 1 (no temperature)."""
-    return _ContrastiveFn.apply(video_features, text_features, None, "mil", group)
+def mil_nce_loss(video_features, text_features, group=None, n_clips=1):
+    """UnivlForVideoTextRetrieval.get_mil_nce_loss (no temperature). video_features [B * n_clips, E] (clips of one video adjacent,
+    as forward_img_encoder returns `clip_feature`), text_features [B, E]."""
+    if n_clips == 1:
+        return _ContrastiveFn.apply(video_features, text_features, None, "mil", group)
+    if video_features.shape[0] != text_features.shape[0] * n_clips:
+        raise ValueError("mil_nce_loss: video_features must hold n_clips rows per text row")
+    return _MilNceClipsFn.apply(video_features.contiguous(), text_features.contiguous(), int(n_clips), group)

@@ -196,6 +196,55 @@ static inline int grid_for(int64_t work_items, int threads = 256, int waves = 8)
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(work_items, threads), static_cast<int64_t>(sm_count()) * waves)));
 }
 
+// masked mean over the P positions (frames x grid cells) of each clip: y[r, :] = sum_p valid[r,p] * x[r,p,:] / count[r]
+// (frame pooling of UnivlVideoBase.forward_img_encoder, prj/base_vtp/roi_univl/univl/model/univl_video_base.py:91-95);
+// pad[r,p] != 0 marks a padded position; inv_count[r] = 1 / #valid is kept for backward. One thread per 8 columns.
+__global__ void __launch_bounds__(256) masked_mean_fwd_kernel(const uint4* __restrict__ x, const uint8_t* __restrict__ pad, uint4* __restrict__ y,
+                                                              float* __restrict__ inv_count, int64_t R, int32_t P, int32_t W8) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < R * W8; i += gridDim.x * 256ll) {
+    const int64_t r = i / W8;
+    const int c = static_cast<int>(i - r * W8);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+    for (int p = 0; p < P; ++p) {
+      if (pad != nullptr && pad[r * P + p]) continue;
+      ++cnt;
+      float v[8];
+      unpack8e(x[(r * P + p) * W8 + c], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    const float inv = 1.f / static_cast<float>(cnt);  // an all-padded clip gives inf/nan like the reference's 0/0
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    y[i] = pack8e(acc);
+    if (c == 0) inv_count[r] = inv;
+  }
+}
+
+// dx[r,p,:] = valid[r,p] * inv_count[r] * dy[r,:]
+__global__ void __launch_bounds__(256) masked_mean_bwd_kernel(const uint4* __restrict__ dy, const uint8_t* __restrict__ pad,
+                                                              const float* __restrict__ inv_count, uint4* __restrict__ dx, int64_t R, int32_t P,
+                                                              int32_t W8) {
+  const int64_t total = R * P * W8;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int64_t rp = i / W8;
+    const int c = static_cast<int>(i - rp * W8);
+    const int64_t r = rp / P;
+    float v[8];
+    if (pad != nullptr && pad[rp]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    } else {
+      unpack8e(dy[r * W8 + c], v);
+      const float inv = inv_count[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= inv;
+    }
+    dx[i] = pack8e(v);
+  }
+}
+
 }  // namespace b200mm
 
 using namespace b200mm;
@@ -287,4 +336,25 @@ extern "C" int b200mm_ema_update(float* pk, const void* pq, int32_t pq_is_bf16, 
   else
     ema_update_kernel<<<grid_for(n), 256, 0, STREAM(stream)>>>(pk, reinterpret_cast<const float*>(pq), n, m);
   return check_launch("ema_update_kernel");
+}
+
+extern "C" int b200mm_masked_mean_fwd(const void* x, const uint8_t* pad, void* y, float* inv_count, int64_t R, int32_t P, int32_t W, void* stream) {
+  B200MM_REQUIRE(x && y && inv_count && R > 0 && P > 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "masked_mean_fwd: R=%lld P=%d W=%d (W %% 8 == 0)",
+                 (long long)R, P, W);
+  const int64_t n = R * (W / 8);
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  masked_mean_fwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(x), pad, reinterpret_cast<uint4*>(y),
+                                                                                     inv_count, R, P, W / 8);
+  return check_launch("masked_mean_fwd_kernel");
+}
+
+extern "C" int b200mm_masked_mean_bwd(const void* dy, const uint8_t* pad, const float* inv_count, void* dx, int64_t R, int32_t P, int32_t W,
+                                      void* stream) {
+  B200MM_REQUIRE(dy && dx && inv_count && R > 0 && P > 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "masked_mean_bwd: R=%lld P=%d W=%d (W %% 8 == 0)",
+                 (long long)R, P, W);
+  const int64_t n = R * P * (W / 8);
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  masked_mean_bwd_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(dy), pad, inv_count,
+                                                                                     reinterpret_cast<uint4*>(dx), R, P, W / 8);
+  return check_launch("masked_mean_bwd_kernel");
 }

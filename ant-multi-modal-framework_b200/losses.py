@@ -32,8 +32,14 @@ class B200ClipNCELoss(nn.Module):
 
 @registry.register_loss("b200_mil_nce")
 class B200MilNCELoss(nn.Module):
-    """get_mil_nce_loss (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197, n_clips = 1) on
-    `video_features` / `text_features` [B, E]; the all-gather of both modalities is fused in."""
+    """get_mil_nce_loss (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197) on `video_features` [B * n_clips, E]
+    (clips of a video adjacent) / `text_features` [B, E]; `n_clips` from the constructor or model_output["n_clips"]; the all-gather of
+    both modalities is fused in."""
+
+    def __init__(self, n_clips=1, **params):
+        super().__init__()
+        self.n_clips = n_clips
 
     def forward(self, sample_list, model_output, *args, **kwargs):
-        return mil_nce_loss(_feat(model_output["video_features"]), _feat(model_output["text_features"]))
+        n = int(model_output.get("n_clips", self.n_clips)) if hasattr(model_output, "get") else self.n_clips
+        return mil_nce_loss(_feat(model_output["video_features"]), _feat(model_output["text_features"]), n_clips=n)

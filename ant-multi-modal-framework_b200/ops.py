@@ -355,6 +355,32 @@ def contrast_rank(a, b, alpha, ref, diag_off=0, gt_col=None, b_mn=False):
     return rank
 
 
+def masked_mean_fwd(x, pad):
+    """x [R, P, W] bf16, pad [R, P] bool/uint8 (True = padded) or None -> (y [R, W] bf16, inv_count [R] f32)."""
+    lib = _lib.load()
+    _req(x, "x", BF16, 3)
+    x = x.contiguous()
+    R, P, W = x.shape
+    if pad is not None:
+        pad = _req(pad, "pad", None, 2).to(torch.uint8).contiguous()
+    y = torch.empty((R, W), device=x.device, dtype=BF16)
+    inv = torch.empty(R, device=x.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_masked_mean_fwd(_ptr(x), _ptr(pad), _ptr(y), _ptr(inv), R, P, W, _stream()), "b200mm_masked_mean_fwd")
+    _count(1)
+    return y, inv, pad
+
+
+def masked_mean_bwd(dy, pad, inv, P):
+    lib = _lib.load()
+    _req(dy, "dy", BF16, 2)
+    dy = dy.contiguous()
+    R, W = dy.shape
+    dx = torch.empty((R, P, W), device=dy.device, dtype=BF16)
+    _lib.check(lib.b200mm_masked_mean_bwd(_ptr(dy), _ptr(pad), _ptr(inv), _ptr(dx), R, P, W, _stream()), "b200mm_masked_mean_bwd")
+    _count(1)
+    return dx
+
+
 def rowdot(a, b, scale=1.0):
     """out[r] = scale * <a[r], b[r]> (f32)."""
     lib = _lib.load()

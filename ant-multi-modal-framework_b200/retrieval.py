@@ -51,8 +51,8 @@ def recall_from_ranks(ranks: torch.Tensor, eps: float = 1e-10) -> Dict[str, floa
     (mean of the two middle values), recall = count / (n + eps)."""
     r = ranks.to(torch.float64)
     n = r.numel()
-    return {"mr": float(torch.quantile(r, 0.5)) + 1.0, "r@1": float((r < 1).sum() / (n + eps)), "r@5": float((r < 5).sum() / (n + eps)),
-            "r@10": float((r < 10).sum() / (n + eps))}
+    return {"mr": float(torch.quantile(r, 0.5)) + 1.0, "r@1": int((r < 1).sum()) / (n + eps), "r@5": int((r < 5).sum()) / (n + eps),
+            "r@10": int((r < 10).sum()) / (n + eps)}
 
 
 def cal_recall(text_emb: torch.Tensor, visual_emb: torch.Tensor) -> Dict[str, float]:
@@ -77,7 +77,7 @@ def cal_sym_recall(text_emb: torch.Tensor, visual_emb: torch.Tensor, t2v: List[L
     for tag, q, k, gts in (("t2v", text_emb, visual_emb, t2v), ("v2t", visual_emb, text_emb, v2t)):
         best = _best_rank(q, k, gts).to(torch.float64)
         n = best.numel()
-        r1, r5, r10 = (float((best < kk).sum()) / n for kk in (1, 5, 10))
+        r1, r5, r10 = (int((best < kk).sum()) / n for kk in (1, 5, 10))
         out.update({f"{tag}-mean_recall": (r1 + r5 + r10) / 3.0, f"{tag}-r@1": r1, f"{tag}-r@5": r5, f"{tag}-r@10": r10,
                     f"{tag}-mr": float(torch.quantile(best, 0.5)) + 1.0})
     return out

@@ -151,6 +151,11 @@ int b200mm_contrast_rank(const void* a, int64_t lda, const void* b, int64_t ldb,
 /* ---------------------------------------------------------------------------------------------
  * Small HBM-bound helpers.
  * ------------------------------------------------------------------------------------------- */
+/* Frame pooling (UnivlVideoBase.forward_img_encoder, prj/base_vtp/roi_univl/univl/model/univl_video_base.py:91-95):
+ * y[r,:] = mean over the non-padded positions p of x[r,p,:]; x [R,P,W] bf16, pad [R,P] bytes (!= 0: padded) or null, W % 8 == 0;
+ * inv_count[r] = 1/#valid (f32, consumed by the backward: dx[r,p,:] = valid * inv_count[r] * dy[r,:]). */
+int b200mm_masked_mean_fwd(const void* x, const uint8_t* pad, void* y, float* inv_count, int64_t R, int32_t P, int32_t W, void* stream);
+int b200mm_masked_mean_bwd(const void* dy, const uint8_t* pad, const float* inv_count, void* dx, int64_t R, int32_t P, int32_t W, void* stream);
 /* y = act(x), bf16, n % 8 == 0 (activation recompute in backward: QuickGELU clip/model.py:222-224, erf-GELU modeling_bert.py:31-37) */
 int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream);
 /* out[(row % period), :] += in[row, :]  (f32 atomics, caller zero-fills): period 1 = bias gradient of nn.Linear,

@@ -106,6 +106,16 @@ def make_losses():
     loss = fn.get_mil_nce_loss(None, sim, B, 1)
     loss.backward()
     out["mil_b37"] = dict(t=t.detach(), v=v.detach(), loss=loss.detach(), dt=t.grad.clone(), dv=v.grad.clone())
+    # n_clips > 1, exactly as forward_stage1 drives it (univl_video_ret.py:357-387): repeat the text rows, then get_mil_nce_loss
+    for key, (B, n, D, seed) in {"mil_b3_n2": (3, 2, 8, 5), "mil_b6_n3": (6, 3, 16, 6), "mil_b9_n4": (9, 4, 12, 7)}.items():
+        torch.manual_seed(seed)
+        t = F.normalize(torch.randn(B, D)).requires_grad_()
+        v = F.normalize(torch.randn(B * n, D)).requires_grad_()
+        l1 = fn.get_l1_simi_matrix(None, t, v, n, True)                     # [B, B, n]
+        mil = l1.unsqueeze(1).repeat([1, n, 1, 1]).view(B * n, B * n)
+        loss = fn.get_mil_nce_loss(None, mil, B, n)
+        loss.backward()
+        out[key] = dict(t=t.detach(), v=v.detach(), n=n, loss=loss.detach(), dt=t.grad.clone(), dv=v.grad.clone())
     # moco
     import types
 
@@ -145,6 +155,9 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "--retrieval-only" in sys.argv:
         make_retrieval()
+        sys.exit(0)
+    if "--losses-only" in sys.argv:
+        make_losses()
         sys.exit(0)
     make_cnclip("cnclip_tiny.pt", TINY, B=6, L=16, vocab_used=512)
     h80 = dict(TINY, vision_width=160, vision_head_width=80, vision_layers=1, text_hidden_size=32,

@@ -173,6 +173,23 @@ def mil_nce_n1(sim_t2v):
     return (torch.logsumexp(both, dim=1) - torch.diagonal(S)).mean()
 
 
+def mil_nce_clips(sim3):
+    """get_mil_nce_loss as driven by forward_stage1 for n_clips >= 1 (univl_video_ret.py:146-197 and :357-387).
+    sim3[i, j, c] = text_i · clip c of video_j  ([B, B, n], the output of get_l1_simi_matrix). forward_stage1 repeats every text
+    row n times, so in the row of video j / clip c the column block "all texts" holds each S[i, j, c] n times; the block "this text
+    against all clips" has the n clips of its own video masked out. Only the middle clip c = n // 2 of each video is scored:
+        loss = mean_j( log( n * sum_i e^{S[i,j,c]} + sum_{k != j, c'} e^{S[j,k,c']} ) - S[j,j,c] - ln n )."""
+    B, _, n = sim3.shape
+    c = n // 2
+    from_video = sim3[:, :, c].t()                                    # [j, i] = S[i, j, c]
+    own = torch.eye(B, dtype=torch.bool)[:, :, None].expand(B, B, n)
+    from_text = sim3.masked_fill(own, float("-inf")).reshape(B, B * n)  # [j, (k, c')] without video j's own clips
+    lse_v = torch.logsumexp(from_video, dim=1) + torch.log(torch.tensor(float(n)))
+    total = torch.logaddexp(lse_v, torch.logsumexp(from_text, dim=1))
+    pos = from_video[torch.arange(B), torch.arange(B)]
+    return (total - pos - torch.log(torch.tensor(float(n)))).mean()
+
+
 def moco_nce(pos, neg, T):
     """MocoUtils.moco_loss, prj/base_vtp/roi_univl/univl/model/moco_utils.py:71-81:
     mean( LSE([pos, neg]/T) - LSE(pos/T) ); pos [N, P], neg [N, K]."""

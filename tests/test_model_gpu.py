@@ -125,6 +125,31 @@ def test_mil_nce_matches_reference_known_answers(golden_dir):
         assert rel_l2(t.grad, tf.grad) < 1e-2 and rel_l2(v.grad, vf.grad) < 1e-2
 
 
+@pytest.mark.parametrize("key", ["mil_b3_n2", "mil_b6_n3", "mil_b9_n4"])
+def test_mil_nce_n_clips_matches_reference(golden_dir, key):
+    """n_clips > 1 (forward_stage1 + get_mil_nce_loss of the unmodified reference, golden) and a larger seeded case vs the oracle"""
+    from b200mm.contrastive import mil_nce_loss
+
+    c = torch.load(os.path.join(golden_dir, "losses.pt"), weights_only=False)[key]
+    n = c["n"]
+    cases = [(c["t"], c["v"], c["loss"])]
+    g = torch.Generator().manual_seed(n)
+    cases.append((torch.nn.functional.normalize(torch.randn(300, 64, generator=g), dim=-1),
+                  torch.nn.functional.normalize(torch.randn(300 * n, 64, generator=g), dim=-1), None))
+    for t32, v32, golden in cases:
+        t16, v16 = t32.to(BF), v32.to(BF)
+        tf, vf = t16.float().requires_grad_(), v16.float().requires_grad_()
+        ref = restated.mil_nce_clips(restated.l1_simi_matrix(tf, vf, n))
+        ref.backward()
+        t, v = t16.cuda().requires_grad_(), v16.cuda().requires_grad_()
+        loss = mil_nce_loss(v, t, n_clips=n)
+        assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref))), (float(loss), float(ref))
+        if golden is not None:
+            assert abs(float(loss) - float(golden)) < 2e-2 * max(1.0, abs(float(golden)))
+        loss.backward()
+        assert rel_l2(t.grad, tf.grad) < 1e-2 and rel_l2(v.grad, vf.grad) < 1e-2, (rel_l2(t.grad, tf.grad), rel_l2(v.grad, vf.grad))
+
+
 def test_no_cpu_fallback():
     import b200mm
 
@@ -232,3 +257,60 @@ def test_moco_queue_loss_ema_and_enqueue():
     pos_c = (qc.detach().float() * kp.cuda().float()).sum(-1, keepdim=True)
     assert abs(float(l1) - float(restated.moco_nce(pos_c.cpu(), negs.cpu(), T))) < 2e-4 * max(1.0, float(l1))
     assert float(l0) != float(l1)
+
+
+def test_video_heads_frame_pooling_matches_reference_arithmetic():
+    """a11: forward_img_encoder / forward_text_encoder of univl_video_base.py:56-166 (frame mean-pool under the mask, img_proj, normalise)
+    against the reference's own tensor expressions evaluated in fp32 on the same encoder outputs."""
+    from b200mm import video
+
+    torch.manual_seed(0)
+    b, n_clips, n_frames, c, hidden = 3, 2, 4, 32, 48
+
+    class FakeEncoder(torch.nn.Module):  # stands in for VitImageEncoder: returns the structures of clip_visual_encoder.py:73-94
+        out_dim = c
+
+        def __init__(self):
+            super().__init__()
+            self.feat = torch.nn.Parameter(torch.randn(b, n_clips * n_frames, c, 1, 1, device="cuda").to(BF))
+            self.mask = torch.zeros(b, n_clips * n_frames, 1, 1, dtype=torch.bool, device="cuda")
+            self.mask[0, 1] = self.mask[0, 2] = self.mask[2, 7] = True
+
+        def forward(self, image, image_mask):
+            return dict(grid_feature=self.feat, grid_mask=self.mask, grid_feature_with_pos=None)
+
+    enc = FakeEncoder()
+    img_proj = torch.nn.Parameter((torch.randn(c, hidden, device="cuda") * 0.2).to(BF))
+    out = video.forward_img_encoder(enc, None, None, [n_clips] * b, [n_frames] * b, img_proj=img_proj)
+    assert set(out) == {"visual_embed", "visual_mask", "visual_grid_shape", "clip_feature"}
+    assert out["visual_embed"].shape == (b, n_clips, hidden) and out["clip_feature"].shape == (b * n_clips, hidden)
+    assert out["visual_mask"].dtype == torch.bool and not out["visual_mask"].any() and tuple(out["visual_grid_shape"]) == (1, 1)
+    # reference expressions (univl_video_base.py:70-73, :84-95, :114) in fp32
+    feat32 = enc.feat.detach().float().requires_grad_()
+    proj32 = img_proj.detach().float().requires_grad_()
+    gf = torch.einsum("bnchw, cj -> bnjhw", feat32, proj32)
+    gf = gf.contiguous().view(b * n_clips, n_frames, *gf.shape[2:])
+    gm = enc.mask.contiguous().view(b * n_clips, n_frames, 1, 1)
+    g = gf.transpose(1, 2).flatten(2)
+    m = ~gm.flatten(1).unsqueeze(1).expand_as(g)
+    clip = (g * m).sum(-1) / m.sum(-1)
+    ref_tokens = clip.view(b, n_clips, hidden)
+    ref_feat = torch.nn.functional.normalize(clip, p=2, dim=-1)
+    assert rel_l2(out["visual_embed"], ref_tokens) < 1e-2
+    assert rel_l2(out["clip_feature"], ref_feat) < 1e-2
+    w = torch.randn_like(ref_feat)
+    (out["clip_feature"].float() * w).sum().backward()
+    (ref_feat * w).sum().backward()
+    assert rel_l2(enc.feat.grad, feat32.grad) < 2e-2, rel_l2(enc.feat.grad, feat32.grad)
+    assert rel_l2(img_proj.grad, proj32.grad) < 2e-2
+    # masked frames receive exactly zero gradient
+    assert float(enc.feat.grad[0, 1].abs().max()) == 0.0 and float(enc.feat.grad[2, 7].abs().max()) == 0.0
+
+    class FakeText(torch.nn.Module):
+        def forward(self, input_ids, attention_mask):
+            torch.manual_seed(1)
+            return torch.randn(4, 6, 16, device="cuda").to(BF), torch.randn(4, 16, device="cuda").to(BF)
+
+    t = video.forward_text_encoder(FakeText(), torch.zeros(4, 6, dtype=torch.long, device="cuda"), torch.ones(4, 6, device="cuda"))
+    assert set(t) == {"sequence_output", "pooled_output", "input_mask", "words_importance"} and t["words_importance"] is None
+    assert float((t["pooled_output"].float().norm(dim=-1) - 1).abs().max()) < 1e-2

@@ -46,6 +46,19 @@ def test_restated_losses_match_golden(golden_dir):
         loss.backward()
         torch.testing.assert_close(t.grad, c["dt"], rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(v.grad, c["dv"], rtol=1e-4, atol=1e-6)
+    # n_clips > 1 (forward_stage1's repeat + get_mil_nce_loss of the unmodified reference)
+    for key in ["mil_b3_n2", "mil_b6_n3", "mil_b9_n4"]:
+        c = fx[key]
+        t = c["t"].clone().requires_grad_()
+        v = c["v"].clone().requires_grad_()
+        loss = restated.mil_nce_clips(restated.l1_simi_matrix(t, v, c["n"]))
+        torch.testing.assert_close(loss, c["loss"], rtol=1e-5, atol=1e-6)
+        loss.backward()
+        torch.testing.assert_close(t.grad, c["dt"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(v.grad, c["dv"], rtol=1e-4, atol=1e-6)
+    # n = 1 is the same function
+    c = fx["mil_b37"]
+    torch.testing.assert_close(restated.mil_nce_clips(restated.l1_simi_matrix(c["t"], c["v"], 1)), c["loss"], rtol=1e-5, atol=1e-6)
     # SURVEY.md §8c known answer (1)
     assert abs(float(fx["mil_b4"]["loss"]) - 2.0541925) < 1e-6
     assert abs(float(fx["mil_b4"]["dt"].abs().sum()) - 2.4046431) < 1e-5

@@ -70,13 +70,16 @@ def time_it(fn, iters):
 if __name__ == "__main__":
     iters = 10
     shapes = [(128, 257, 16, 64, False), (256, 77, 12, 64, True)]
-    for c in CASES:
+    for c in CASES + [(5, 32, 2, 64, True), (3, 320, 2, 64, False), (300, 257, 16, 64, False)]:
         check_fwd(*c)
-    for B, L, H, hd, m in shapes:
+    for B, L, H, hd, m in shapes + [(1024, 257, 16, 64, False)]:
         qkv, d_o, kb = make(B, L, H, hd, m)
         t = time_it(lambda: ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb), iters)
+        t1 = legacy(lambda: time_it(lambda: ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb), iters), "B200MM_ATTN_FWD_V1")
         fl = 4.0 * B * H * L * L * hd
-        print(f"time fwd B={B} L={L} H={H}: {t:.3f} ms ({fl / t / 1e9:.0f} TF/s)", flush=True)
+        print(f"time fwd B={B} L={L} H={H}: {t:.3f} ms ({fl / t / 1e9:.0f} TF/s)   [v1 kernel: {t1:.3f} ms]", flush=True)
+    if "--fwd-only" in sys.argv:
+        sys.exit(0)
     for c in CASES:
         check_bwd(*c)
     for B, L, H, hd, m in shapes:

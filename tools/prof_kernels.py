@@ -17,7 +17,7 @@ b = torch.zeros(W, device="cuda", dtype=BF)
 wfc = (torch.randn(4 * W, W, device="cuda") * 0.02).to(BF)
 bfc = torch.zeros(4 * W, device="cuda", dtype=BF)
 wproj = (torch.randn(W, 4 * W, device="cuda") * 0.02).to(BF)
-for rep in range(2):
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     # LayerNorm fwd / bwd
     y, _, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5)
     dw = torch.zeros(W, device="cuda")
