@@ -37,6 +37,7 @@ struct AttnTcParams {
   int32_t B, H, L, Lk;  // Lk = L rounded up to 16
   int32_t q_off, k_off, v_off;
   float scale;
+  int32_t short_max;  // tiles with <= short_max valid rows take the replicated-rows path (32, or 0 = off)
 };
 
 enum { BAR_K_FULL = 0, BAR_K_EMPTY, BAR_V_FULL, BAR_V_EMPTY, BAR_Q_FULL0, BAR_Q_FULL1, BAR_Q_EMPTY0, BAR_Q_EMPTY1, BAR_S_FULL, BAR_P_FULL,
@@ -336,8 +337,8 @@ enum { F2_KA_FULL = 0, F2_KA_EMPTY, F2_KB_FULL, F2_KB_EMPTY, F2_VA_FULL, F2_VA_E
 constexpr int A2_THREADS = 96 + AT_SM_THREADS;  // warps 0..2 = TMA / MMA / TMEM allocator, warps 3..18 = softmax (19 warps: 104 registers each)
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
-attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKa,
-                    const __grid_constant__ CUtensorMap tmKb, const AttnTcParams p) {
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ32,
+                    const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[F2_COUNT];
   __shared__ uint32_t tmem_base_smem;
@@ -353,7 +354,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* v_sm = k_sm + kv_pad;
   uint8_t* q_sm = v_sm + kv_pad;                     // 2 x 16 KB
   uint8_t* p_sm = q_sm + 2 * 16384;                  // n_ptiles x 16 KB
-  float* bias_sm = reinterpret_cast<float*>(p_sm + n_ptiles * 16384);  // [2][Lk] key bias * log2e, -inf for key >= L
+  uint8_t* o_sm = p_sm + n_ptiles * 16384;           // 16 KB staging tile of the output epilogue
+  float* bias_sm = reinterpret_cast<float*>(o_sm + 16384);  // [2][Lk] key bias * log2e, -inf for key >= L
   float* red_max = bias_sm + 2 * Lk;    // [2][4][128]
   float* red_sum = red_max + 2 * 512;   // [2][4][128]
 
@@ -406,7 +408,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait_relaxed(&bars[F2_Q_EMPTY0 + qb], ((g >> 1) & 1) ^ 1);
       if (lane == 0) {
         mbar_expect_tx(&bars[F2_Q_FULL0 + qb], 16384);
-        tma_load_2d(&tmQ, &bars[F2_Q_FULL0 + qb], q_sm + qb * 16384, p.q_off + h * AT_HD, row0 + tk * 128);
+        if (p.L - tk * 128 > p.short_max) {
+          tma_load_2d(&tmQ, &bars[F2_Q_FULL0 + qb], q_sm + qb * 16384, p.q_off + h * AT_HD, row0 + tk * 128);
+        } else {
+          // short tile (<= 32 valid query rows, e.g. the 257th token): the same 32 rows go to all four lane quarters, so that the
+          // softmax warps of every scheduler can share the columns of these few rows instead of one quarter doing all the work
+#pragma unroll
+          for (int rep = 0; rep < 4; ++rep)
+            tma_load_2d(&tmQ32, &bars[F2_Q_FULL0 + qb], q_sm + qb * 16384 + rep * 4096, p.q_off + h * AT_HD, row0 + tk * 128);
+        }
       }
       if (tk == 0) {
         mbar_wait_relaxed(&bars[F2_VA_EMPTY], ipar);
@@ -632,6 +642,131 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld_32x16(tmem_o0 + ob * 64 + lane_addr + part * 16, v);
         tmem_ld_wait16(v);
         const int q_row = tk * 128 + r;
+        // a thread's 16 columns are only 32 B of its row: the quarter's 32 rows are staged as bf16 and written back by the same
+        // four warps as full 128-byte rows (direct 32-byte stores cost 32 lines per warp instruction)
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+        *reinterpret_cast<uint4*>(o_sm + sw128_off(r, part * 2)) = o;
+        o.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+        *reinterpret_cast<uint4*>(o_sm + sw128_off(r, part * 2 + 1)) = o;
+        if (part == 0 && q_row < p.L) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.L + q_row] = (m_row + log2f(sum)) / AT_LOG2E;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[F2_O_EMPTY0 + ob]);
+        quarter_sync();
+        __nv_bfloat16* obase = p.o + (static_cast<int64_t>(b) * p.L + tk * 128) * p.ldo + h * AT_HD;
+#pragma unroll
+        for (int it2 = 0; it2 < 2; ++it2) {
+          const int row = quarter * 32 + part * 8 + it2 * 4 + (lane >> 3);
+          const int ch = lane & 7;
+          if (tk * 128 + row < p.L)
+            *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * p.ldo + ch * 8) = *reinterpret_cast<const uint4*>(o_sm + sw128_off(row, ch));
+        }
+        // (the next use of these staging rows is a full tile later: the quarter meets at two max exchanges in between)
+        return;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[F2_O_EMPTY0 + ob]);
+    };
+
+    // ---- short tile (<= 32 valid rows, replicated in all four lane quarters): warp wid owns 16-key chunk wid of the block, every
+    //      lane = one of the 32 rows; row maxima / sums meet across all 16 warps; P goes to rows 0..31 of the tiles
+    const int wid = part * 4 + quarter;
+    auto softmax_block_short = [&](int g, bool blk_b, const float* bias) {
+      mbar_wait(&bars[blk_b ? F2_SB_FULL : F2_SA_FULL], g & 1);
+      tc_fence_after();
+      const int nblk = blk_b ? nb : na;
+      const int kc = (blk_b ? na : 0) + wid;
+      const bool has = wid < nblk;
+      uint32_t v[16];
+      tmem_ld_32x16((blk_b ? tmem_sb : tmem_sa) + lane_addr + (has ? wid : 0) * 16, v);
+      tmem_ld_wait16(v);
+      float mloc = -INFINITY;
+      if (has) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float z = fmaf(__uint_as_float(v[j]), c, bias[kc * 16 + j]);
+          v[j] = __float_as_uint(z);
+          mloc = fmaxf(mloc, z);
+        }
+      }
+      float* rm = red_max + (xcnt & 1) * 512;
+      ++xcnt;
+      rm[wid * 32 + lane] = mloc;
+      full_sync();
+      float bm = rm[lane];
+#pragma unroll
+      for (int w = 1; w < 16; ++w) bm = fmaxf(bm, rm[w * 32 + lane]);
+      float m_new = bm, alpha = 1.f;
+      if (blk_b) {
+        m_new = fmaxf(m_run, bm);
+        alpha = fast_exp2(m_run - m_new);
+        psum *= alpha;
+      } else {
+        psum = 0.f;
+      }
+      m_run = m_new;
+      mbar_wait(&bars[blk_b ? F2_PB_EMPTY : F2_PA_EMPTY], (g & 1) ^ 1);
+      if (has) {
+        float e[16], s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) e[j] = fast_exp2(__uint_as_float(v[j]) - m_new);
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) { s0 += e[j]; s1 += e[j + 1]; }
+        psum += s0 + s1;
+        uint8_t* ptile = p_sm + (kc >> 2) * 16384;
+        const int chunk0 = (kc & 3) * 2;
+        uint4 o;
+        o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+        o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+        *reinterpret_cast<uint4*>(ptile + sw128_off(lane, chunk0)) = o;
+        o.x = pack_bf16x2(e[8], e[9]); o.y = pack_bf16x2(e[10], e[11]);
+        o.z = pack_bf16x2(e[12], e[13]); o.w = pack_bf16x2(e[14], e[15]);
+        *reinterpret_cast<uint4*>(ptile + sw128_off(lane, chunk0 + 1)) = o;
+      }
+      if (blk_b && quarter == 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
+        mbar_wait(&bars[F2_PA_EMPTY], g & 1);  // PV_a(g) has completed
+        tc_fence_after();
+        uint32_t o[16];
+        const uint32_t oaddr = tmem_o0 + (g & 1) * 64 + part * 16;  // lanes 0..31
+        tmem_ld_32x16(oaddr, o);
+        tmem_ld_wait16(o);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+        tmem_st_32x16(oaddr, o);
+        tmem_st_wait();
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[blk_b ? F2_PB_FULL : F2_PA_FULL]);
+    };
+    auto epilogue_short = [&](int g, float m_row, float ps_row) {
+      const int it = g / n_qt, tk = g - it * n_qt;
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / p.H, h = item - b * p.H;
+      const int ob = g & 1;
+      mbar_wait(&bars[F2_O_FULL0 + ob], (g >> 1) & 1);
+      tc_fence_after();
+      float* rs = red_sum + ob * 512;
+      rs[wid * 32 + lane] = ps_row;
+      full_sync();
+      if (quarter == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) sum += rs[w * 32 + lane];
+        const float inv = 1.f / sum;
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_o0 + ob * 64 + part * 16, v);
+        tmem_ld_wait16(v);
+        const int q_row = tk * 128 + lane;
         if (q_row < p.L) {
           __nv_bfloat16* orow = p.o + (static_cast<int64_t>(b) * p.L + q_row) * p.ldo + h * AT_HD + part * 16;
           uint4 o;
@@ -653,9 +788,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(&bars[F2_O_EMPTY0 + ob]);
     };
 
-    bool prev_active = false;
+    bool prev_active = false, prev_short = false;
     for (int g = 0; g < G; ++g) {
       const int it = g / n_qt, tk = g - it * n_qt;
+      const bool short_tile = p.L - tk * 128 <= p.short_max;
       const bool active = tk * 128 + quarter * 32 < p.L;  // warp-uniform: any valid query row in this warp
       const float* bias = bias_sm;
       if (has_bias) {
@@ -666,14 +802,25 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         bias = bias_sm + (it & 1) * Lk;
       }
-      softmax_block(g, false, active, bias);
-      if (g > 0) epilogue(g - 1, prev_active, m_fin, ps_fin);
-      if (nb > 0) softmax_block(g, true, active, bias);
+      if (short_tile) softmax_block_short(g, false, bias);
+      else softmax_block(g, false, active, bias);
+      if (g > 0) {
+        if (prev_short) epilogue_short(g - 1, m_fin, ps_fin);
+        else epilogue(g - 1, prev_active, m_fin, ps_fin);
+      }
+      if (nb > 0) {
+        if (short_tile) softmax_block_short(g, true, bias);
+        else softmax_block(g, true, active, bias);
+      }
       m_fin = m_run;
       ps_fin = psum;
       prev_active = active;
+      prev_short = short_tile;
     }
-    if (G > 0) epilogue(G - 1, prev_active, m_fin, ps_fin);
+    if (G > 0) {
+      if (prev_short) epilogue_short(G - 1, m_fin, ps_fin);
+      else epilogue(G - 1, prev_active, m_fin, ps_fin);
+    }
   }
 
   tc_fence_before();
@@ -687,7 +834,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 static size_t attn_tc2_smem_bytes(int Lk) {
   const int kv_pad = (Lk * 128 + 1023) & ~1023;
   const int n_ptiles = (Lk + 63) / 64;
-  return static_cast<size_t>(2) * kv_pad + 2 * 16384 + static_cast<size_t>(n_ptiles) * 16384 + 2 * Lk * 4 + 4 * 512 * 4 + 1024;
+  return static_cast<size_t>(2) * kv_pad + 2 * 16384 + static_cast<size_t>(n_ptiles + 1) * 16384 + 2 * Lk * 4 + 4 * 512 * 4 + 1024;
 }
 
 static size_t attn_tc_smem_bytes(int Lk) {
@@ -711,6 +858,7 @@ int attention_fwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
   AttnTcParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(o); p.ldo = ldo; p.lse = lse; p.key_bias = key_bias;
   p.B = B; p.H = H; p.L = L; p.Lk = Lk; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.scale = scale;
+  p.short_max = getenv("B200MM_ATTN_NOSHORT") ? 0 : 32;
   const int grid = std::min(B * H, sm_count());
   if (!getenv("B200MM_ATTN_FWD_V1")) {
     const int n_chunks = Lk / 16, na = n_chunks < 8 ? n_chunks : 8, nb = n_chunks - na;
@@ -725,7 +873,10 @@ int attention_fwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
       set_last_error("attention_fwd_tc2: cudaFuncSetAttribute(%zu): %s", smem2, cudaGetErrorString(e2));
       return B200MM_ERR_LAUNCH;
     }
-    attn_fwd_tc2_kernel<<<grid, A2_THREADS, smem2, stream>>>(tmQ, tmKa, tmKb, p);
+    CUtensorMap tmQ32;
+    rc = make_tmap_2d_bf16(&tmQ32, qkv, static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(ld), 64, 32);
+    if (rc) return rc;
+    attn_fwd_tc2_kernel<<<grid, A2_THREADS, smem2, stream>>>(tmQ, tmQ32, tmKa, tmKb, p);
     rc = check_launch("attn_fwd_tc2_kernel");
     return rc ? rc : 1;
   }

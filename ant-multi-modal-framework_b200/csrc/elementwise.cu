@@ -73,8 +73,47 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const __nv_bfloat
     float v[8];
     unpack8e(*reinterpret_cast<const uint4*>(in + row * W + col), v);
     float* o = out + id * W + col;
+    // two 16-byte vector reductions instead of eight scalar atomics
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  }
+}
+
+// same operation for a handful of output rows (token_type_embeddings: 2): every input row would hit the same few addresses, so each
+// thread keeps one accumulator set per output row over its slice of the input and issues NOUT x 2 vector reductions at the end.
+// block = 32 column groups (8 cols) x 8 row lanes; grid = (column blocks, row chunks)
+template <int NOUT>
+__global__ void __launch_bounds__(256) scatter_add_few_kernel(const __nv_bfloat16* __restrict__ in, const int64_t* __restrict__ ids,
+                                                              float* __restrict__ out, int64_t rows, int32_t W, int64_t skip_id,
+                                                              int64_t rows_per_chunk, int32_t n_out) {
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cg) * 8;
+  if (col >= W) return;
+  const int64_t r0 = blockIdx.y * rows_per_chunk;
+  const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  float acc[NOUT][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+  for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+  for (int64_t row = r0 + rl; row < r1; row += 8) {
+    const int64_t id = ids[row];
+    if (id == skip_id || id < 0 || id >= n_out) continue;
+    float v[8];
+    unpack8e(*reinterpret_cast<const uint4*>(in + row * W + col), v);
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+      if (id == o) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o][j] += v[j];
+      }
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    if (o >= n_out) break;
+    float* dst = out + static_cast<int64_t>(o) * W + col;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[o][0]), "f"(acc[o][1]), "f"(acc[o][2]), "f"(acc[o][3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(acc[o][4]), "f"(acc[o][5]), "f"(acc[o][6]), "f"(acc[o][7]) : "memory");
   }
 }
 
@@ -279,7 +318,18 @@ extern "C" int b200mm_scatter_add_rows(const void* in, const int64_t* ids, float
                                        int64_t n_out_rows, void* stream) {
   B200MM_REQUIRE(rows >= 0 && W > 0 && W % 8 == 0, B200MM_ERR_SHAPE, "scatter_add_rows: rows=%lld W=%d", (long long)rows, W);
   if (rows == 0) return B200MM_OK;
-  B200MM_REQUIRE(ALIGNED16(in), B200MM_ERR_ALIGN, "scatter_add_rows: input must be 16B aligned");
+  B200MM_REQUIRE(ALIGNED16(in) && ALIGNED16(out), B200MM_ERR_ALIGN, "scatter_add_rows: input and output must be 16B aligned");
+  if (n_out_rows <= 4) {
+    const int64_t rows_per_chunk = 512;
+    dim3 grid(static_cast<unsigned>((W / 8 + 31) / 32), static_cast<unsigned>((rows + rows_per_chunk - 1) / rows_per_chunk));
+    if (n_out_rows <= 2)
+      scatter_add_few_kernel<2><<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), ids, out, rows, W, skip_id, rows_per_chunk,
+                                                                  static_cast<int32_t>(n_out_rows));
+    else
+      scatter_add_few_kernel<4><<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), ids, out, rows, W, skip_id, rows_per_chunk,
+                                                                  static_cast<int32_t>(n_out_rows));
+    return check_launch("scatter_add_few_kernel");
+  }
   scatter_add_rows_kernel<<<grid_for(rows * (W / 8)), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), ids, out, rows,
                                                                                   W, skip_id, n_out_rows);
   return check_launch("scatter_add_rows_kernel");

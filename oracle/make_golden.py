@@ -107,7 +107,7 @@ def make_losses():
     loss.backward()
     out["mil_b37"] = dict(t=t.detach(), v=v.detach(), loss=loss.detach(), dt=t.grad.clone(), dv=v.grad.clone())
     # n_clips > 1, exactly as forward_stage1 drives it (univl_video_ret.py:357-387): repeat the text rows, then get_mil_nce_loss
-    for key, (B, n, D, seed) in {"mil_b3_n2": (3, 2, 8, 5), "mil_b6_n3": (6, 3, 16, 6), "mil_b9_n4": (9, 4, 12, 7)}.items():
+    for key, (B, n, D, seed) in {"mil_b3_n2": (3, 2, 8, 5), "mil_b6_n3": (6, 3, 16, 6), "mil_b9_n4": (9, 4, 24, 7)}.items():
         torch.manual_seed(seed)
         t = F.normalize(torch.randn(B, D)).requires_grad_()
         v = F.normalize(torch.randn(B * n, D)).requires_grad_()

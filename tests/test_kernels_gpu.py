@@ -195,6 +195,16 @@ def test_small_helpers(ops):
     ref = torch.zeros(9, W).index_add_(0, ids, x.float())
     ref[0] = 0
     close(out, ref, 1e-5, "scatter")
+    # few output rows (token_type_embeddings): register-accumulating kernel; ragged row count, skip id, 2 and 3 output rows
+    for n_out, skip in [(2, -1), (3, 1)]:
+        big = rnd(1500 + n_out, W)
+        ids2 = torch.randint(0, n_out, (big.shape[0],), generator=torch.Generator().manual_seed(n_out))
+        out2 = torch.zeros(n_out, W, device="cuda")
+        ops.scatter_add_rows(big.cuda(), ids2.cuda(), out2, skip_id=skip)
+        ref2 = torch.zeros(n_out, W).index_add_(0, ids2, big.float())
+        if skip >= 0:
+            ref2[skip] = 0
+        close(out2, ref2, 1e-5, f"scatter few rows ({n_out})")
     y, inv = ops.rownorm_fwd(x.cuda())
     xf = x.float().requires_grad_()
     refn = xf / xf.norm(dim=-1, keepdim=True)

@@ -60,8 +60,8 @@ def test_ranks_general_shapes(M, N, E):
     # rows whose positive is within fp32 accumulation noise of another score are ambiguous: exclude them from the exact check
     margin = np.abs(sim - ref[:, None])
     margin[np.arange(M), gt.numpy()] = 1.0
-    clear = margin.min(1) > 1e-5
-    assert clear.mean() > 0.95
+    clear = margin.min(1) > 2e-6
+    assert clear.mean() > 0.9
     assert np.array_equal(ranks[clear], want[clear])
     assert np.abs(ranks[~clear] - want[~clear]).max(initial=0) <= 2
     if M == N:
@@ -69,7 +69,7 @@ def test_ranks_general_shapes(M, N, E):
         d = np.diag(sim)
         w0 = (sim > d[:, None]).sum(1)
         m0 = np.abs(sim - d[:, None]) + np.eye(M)
-        ok = m0.min(1) > 1e-5
+        ok = m0.min(1) > 2e-6
         assert np.array_equal(r0[ok], w0[ok])
 
 

@@ -7,7 +7,7 @@ import torch
 
 from b200mm import ops
 
-CASES = [(1, 128, 1, 64, False), (2, 77, 3, 64, True), (3, 257, 2, 64, False), (2, 288, 2, 64, True), (2, 197, 3, 64, False), (40, 257, 16, 64, False)]
+CASES = [(1, 30, 1, 64, True), (2, 129, 2, 64, False), (3, 160, 2, 64, True), (1, 128, 1, 64, False), (2, 77, 3, 64, True), (3, 257, 2, 64, False), (2, 288, 2, 64, True), (2, 197, 3, 64, False), (40, 257, 16, 64, False)]
 
 
 def make(B, L, H, hd, masked, seed=0):
@@ -77,14 +77,16 @@ if __name__ == "__main__":
         t = time_it(lambda: ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb), iters)
         t1 = legacy(lambda: time_it(lambda: ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb), iters), "B200MM_ATTN_FWD_V1")
         fl = 4.0 * B * H * L * L * hd
-        print(f"time fwd B={B} L={L} H={H}: {t:.3f} ms ({fl / t / 1e9:.0f} TF/s)   [v1 kernel: {t1:.3f} ms]", flush=True)
+        t2 = legacy(lambda: time_it(lambda: ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb), iters), "B200MM_ATTN_NOSHORT")
+        print(f"time fwd B={B} L={L} H={H}: {t:.3f} ms ({fl / t / 1e9:.0f} TF/s)   [v1 kernel: {t1:.3f} ms; v2 without short-tile path: {t2:.3f} ms]", flush=True)
     if "--fwd-only" in sys.argv:
         sys.exit(0)
     for c in CASES:
         check_bwd(*c)
-    for B, L, H, hd, m in shapes:
+    for B, L, H, hd, m in shapes + [(1024, 257, 16, 64, False)]:
         qkv, d_o, kb = make(B, L, H, hd, m)
         o, lse = ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb)
         t = time_it(lambda: ops.attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=kb), iters)
         fl = 10.0 * B * H * L * L * hd
-        print(f"time bwd B={B} L={L} H={H}: {t:.3f} ms ({fl / t / 1e9:.0f} TF/s alg)", flush=True)
+        t2 = legacy(lambda: time_it(lambda: ops.attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=kb), iters), "B200MM_ATTN_NOSHORT")
+        print(f"time bwd B={B} L={L} H={H}: {t:.3f} ms ({fl / t / 1e9:.0f} TF/s alg)   [without short-tile path: {t2:.3f} ms]", flush=True)
