@@ -860,7 +860,9 @@ int attention_fwd_tc(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
   p.B = B; p.H = H; p.L = L; p.Lk = Lk; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.scale = scale;
   p.short_max = getenv("B200MM_ATTN_NOSHORT") ? 0 : 32;
   const int grid = std::min(B * H, sm_count());
-  if (!getenv("B200MM_ATTN_FWD_V1")) {
+  // sequences of <= 128 keys are a single key block: nothing to pipeline, the first-generation kernel (one S buffer, two passes) is
+  // measured faster there (BERT, L = 77: 0.065 vs 0.074 ms at 256 x 12 heads); longer ones take the key-blocked kernel
+  if (!getenv("B200MM_ATTN_FWD_V1") && Lk > 128) {
     const int n_chunks = Lk / 16, na = n_chunks < 8 ? n_chunks : 8, nb = n_chunks - na;
     CUtensorMap tmKa, tmKb;
     rc = make_tmap_2d_bf16(&tmKa, qkv, static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(ld), 64, na * 16);

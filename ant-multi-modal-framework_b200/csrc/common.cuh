@@ -138,6 +138,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// variant for waits that are expected to be long (epilogue warps waiting for an accumulator): the hardware suspends the thread for
+// up to `ns` nanoseconds per attempt instead of spinning through issue slots — the GPU runs at its power cap in these kernels, and
+// idle spinning is paid for in SM clock
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (!ok);
+}
 // variant for the single-purpose producer / issuer warps: back off between polls so that their spinning does not take issue
 // slots from the epilogue warps on the same scheduler
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {

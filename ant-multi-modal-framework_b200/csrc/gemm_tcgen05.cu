@@ -83,11 +83,22 @@ struct ContrastParams {
 
 enum { EPI_STD = 0, EPI_LSE = 1, EPI_SOFTGRAD = 2, EPI_RANK = 3 };
 
+// epilogue wait policy: B200MM_GEMM_WAIT_NS=0 spins, otherwise the suspend hint in ns (default below)
+static uint32_t gemm_wait_ns() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200MM_GEMM_WAIT_NS");
+    v = e ? atoi(e) : 2000;
+  }
+  return static_cast<uint32_t>(v);
+}
+
 struct GemmParams {
   int64_t M, N, K;
   int32_t m_tiles, n_tiles, splits, kb_total, kb_per_split;
   float* partial;  // split-K: f32 [splits][M][N]; nullptr when splits == 1
   uint32_t mn_lbo, mn_sbo, k_lbo, k_sbo;  // descriptor byte offsets (defaults below; env-overridable for bring-up)
+  uint32_t wait_ns;  // > 0: epilogue warps wait for the accumulator with a suspending try_wait (hint in ns) instead of spinning
   EpiParams epi;
   ContrastParams con;
 };
@@ -103,7 +114,7 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
     v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
     v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
   }
-  if (e.aux_out != nullptr) {
+  if (e.aux_out != nullptr && e.dact_in == nullptr) {
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
     o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
@@ -115,6 +126,12 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
     float x[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= apply_dact(e.act, x[j]);
+    if (e.aux_out != nullptr) {  // with dact_in the auxiliary output is the recomputed activation act(u)
+      uint4 o;
+      o.x = pack_bf16x2(apply_act(e.act, x[0]), apply_act(e.act, x[1])); o.y = pack_bf16x2(apply_act(e.act, x[2]), apply_act(e.act, x[3]));
+      o.z = pack_bf16x2(apply_act(e.act, x[4]), apply_act(e.act, x[5])); o.w = pack_bf16x2(apply_act(e.act, x[6]), apply_act(e.act, x[7]));
+      *reinterpret_cast<uint4*>(e.aux_out + m * e.ldd + n) = o;
+    }
   } else if (e.act != B200MM_ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = apply_act(e.act, v[j]);
@@ -159,7 +176,7 @@ __device__ __forceinline__ void epi_lean8(float (&v)[8], const EpiFlags& f, floa
     v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
     v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
   }
-  if (f.has_aux) {
+  if (f.has_aux && !f.has_dact) {
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
     o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
@@ -169,12 +186,33 @@ __device__ __forceinline__ void epi_lean8(float (&v)[8], const EpiFlags& f, floa
     const float2 x0 = unpack_bf16x2(ext8.x), x1 = unpack_bf16x2(ext8.y), x2 = unpack_bf16x2(ext8.z), x3 = unpack_bf16x2(ext8.w);
     const float x[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
     if (f.has_dact) {
+      // with aux_out the activation act(u) itself is emitted next to D = acc * act'(u): both share the sigmoid / Gaussian terms, and
+      // the backward pass gets the activated hidden (operand of the following weight gradient) without a separate recompute kernel
+      float g[8];
       if (f.act == B200MM_ACT_QUICKGELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dact_quickgelu(x[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float sg = sigmoid_1702(x[j]);
+          g[j] = x[j] * sg;
+          v[j] *= sg * fmaf(1.702f * x[j], 1.f - sg, 1.f);
+        }
       } else if (f.act == B200MM_ACT_GELU_ERF) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dact_gelu_erf(x[j]);
+        for (int j = 0; j < 8; ++j) {
+          float cdf, expo;
+          gauss_cdf_pdf(x[j], cdf, expo);
+          g[j] = x[j] * cdf;
+          v[j] *= fmaf(x[j] * 0.3989422804014327f, expo, cdf);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = x[j];
+      }
+      if (f.has_aux) {
+        uint4 o;
+        o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+        o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+        *reinterpret_cast<uint4*>(auxptr) = o;
       }
     } else {
       if (f.act == B200MM_ACT_QUICKGELU) {
@@ -428,7 +466,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if constexpr (EPI == EPI_STD) {
         if (fl.has_bias && n0 + cpart * 32 + cg < p.N) nxt_bias = *reinterpret_cast<const uint4*>(p.epi.bias + n0 + cpart * 32 + cg);
       }
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (p.wait_ns) mbar_wait_suspend(&tmem_full_bar[acc], acc_phase, p.wait_ns);
+      else mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if constexpr (EPI == EPI_STD) {
@@ -732,6 +771,7 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
     p.partial = reinterpret_cast<float*>(a->workspace);
   }
   p.mn_lbo = SLAB_BYTES; p.mn_sbo = 1024; p.k_lbo = 16; p.k_sbo = 1024;
+  p.wait_ns = gemm_wait_ns();
   if (const char* dbg = getenv("B200MM_DBG_DESC")) {  // bring-up only: "mn_lbo,mn_sbo,k_lbo,k_sbo" in bytes
     unsigned v[4];
     if (sscanf(dbg, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]) == 4) { p.mn_lbo = v[0]; p.mn_sbo = v[1]; p.k_lbo = v[2]; p.k_sbo = v[3]; }
@@ -775,6 +815,8 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
     B200MM_TRY(0, 1, false, false, true, false, false, false, B200MM_ACT_NONE)       // dgrad + residual-branch gradient
     B200MM_TRY(0, 1, false, false, false, true, false, false, B200MM_ACT_QUICKGELU)  // dgrad through QuickGELU
     B200MM_TRY(0, 1, false, false, false, true, false, false, B200MM_ACT_GELU_ERF)   // dgrad through erf-GELU
+    B200MM_TRY(0, 1, false, true, false, true, false, false, B200MM_ACT_QUICKGELU)   // ... also emitting act(u) (activation recompute)
+    B200MM_TRY(0, 1, false, true, false, true, false, false, B200MM_ACT_GELU_ERF)
     else done = false;
 #undef B200MM_TRY
     if (done) {
@@ -817,6 +859,7 @@ static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const 
   p.splits = 1;
   p.partial = nullptr;
   p.mn_lbo = SLAB_BYTES; p.mn_sbo = 1024; p.k_lbo = 16; p.k_sbo = 1024;
+  p.wait_ns = gemm_wait_ns();
   p.epi.alpha = alpha;
   int rc = make_tmap_2d_bf16(&tmA, a, K, M, lda, BK, BM);
   if (rc) return rc;

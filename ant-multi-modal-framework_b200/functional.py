@@ -94,11 +94,13 @@ class VitBlockFn(Function):
         vg = _VecGrads(x.device, [W, W, 3 * W, W, W, W, 4 * W, W])  # ln1 w,b | in_b | out_b | ln2 w,b | fc_b | proj_b
         # ---- MLP branch
         if g is None:
-            g = ops.act_fwd(u, ACT_QUICKGELU)
+            # the dgrad GEMM emits the activated hidden act(u) next to du (same sigmoid): no separate recompute pass over [T, 4W]
+            du, g = ops.gemm(dy, proj_w, b_mn=True, act=ACT_QUICKGELU, dact_in=u, aux_out=True)
+        else:
+            du = ops.gemm(dy, proj_w, b_mn=True, act=ACT_QUICKGELU, dact_in=u)
         d_proj_w = _wgrad(dy, g)
         del g
         ops.rowsum_periodic(dy, vg[7])
-        du = ops.gemm(dy, proj_w, b_mn=True, act=ACT_QUICKGELU, dact_in=u)
         h2, _, _, _ = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
         d_fc_w = _wgrad(du, h2)
         del h2
@@ -249,11 +251,10 @@ class BertLayerFn(Function):
         I = i_w.shape[0]
         vg = _VecGrads(x.device, [3 * Hd, Hd, Hd, Hd, I, Hd, Hd, Hd])  # qkv_b | o_b | ln1 w,b | i_b | d_b | ln2 w,b
         ds2 = ops.layernorm_bwd(dy.contiguous(), s2, mean2, rstd2, ln2_w, vg[6], vg[7])
-        g = ops.act_fwd(u, ACT_GELU_ERF)
+        du, g = ops.gemm(ds2, d_w, b_mn=True, act=ACT_GELU_ERF, dact_in=u, aux_out=True)  # g = gelu(u) recomputed in the epilogue
         d_d_w = _wgrad(ds2, g)
         del g
         ops.rowsum_periodic(ds2, vg[5])
-        du = ops.gemm(ds2, d_w, b_mn=True, act=ACT_GELU_ERF, dact_in=u)
         x1, _, _, _ = ops.layernorm_fwd(s1, ln1_w, ln1_b, eps)
         d_i_w = _wgrad(du, x1)
         del x1

@@ -49,8 +49,9 @@ int b200mm_check_device(void);
  *   b_mn == 0: B is row-major [N, K] with row pitch ldb      (nn.Linear.weight layout)
  *   b_mn == 1: B is row-major [K, N] with row pitch ldb
  * Epilogue, per element, in this order (fp32):
- *   v = alpha*acc; v += bias[n] (bf16, optional); if aux_out: aux_out[m,n] = v (bf16, pre-activation);
- *   v = act(v); if dact_in: v *= act'(dact_in[m,n]) (act is then applied as derivative only, not to v);
+ *   v = alpha*acc; v += bias[n] (bf16, optional); if aux_out (without dact_in): aux_out[m,n] = v (bf16, pre-activation);
+ *   v = act(v); if dact_in: v *= act'(dact_in[m,n]) (act is then applied as derivative only, not to v), and with aux_out
+ *   also aux_out[m,n] = act(dact_in[m,n]) (bf16: the activation recomputed for the weight gradient that follows);
  *   v += residual[m,n] (bf16, optional; not together with dact_in); D[m,n] = v (bf16 if d_f32 == 0 else f32)
  * splits > 1 partitions K over `splits` CTAs per tile; partial sums go to `workspace`
  * (f32, >= b200mm_gemm_workspace_bytes) and a second kernel reduces them and applies the epilogue.
@@ -69,7 +70,7 @@ typedef struct {
   float alpha;
   const void* bias;     /* bf16 [N] or NULL */
   int32_t act;          /* B200MM_ACT_* */
-  void* aux_out;        /* bf16 [M,N] pitch ldd, pre-activation copy, or NULL */
+  void* aux_out;        /* bf16 [M,N] pitch ldd: pre-activation copy (act(dact_in) when dact_in is set), or NULL */
   const void* dact_in;  /* bf16 [M,N] pitch ld_dact: multiply by act'(dact_in) instead of applying act */
   int64_t ld_dact;
   const void* residual; /* bf16 [M,N] pitch ldr or NULL */

@@ -81,6 +81,15 @@ def test_gemm_epilogue(ops, act):
     ref_d = (a.float() @ w.float().t()) * uf.grad
     got_d = ops.gemm(a.cuda(), w.cuda(), act=act, dact_in=u.cuda(), out_f32=True)
     close(got_d, ref_d, 3e-5, "dact")
+    # ... and with aux_out the same launch also returns the recomputed activation act(u) (bf16)
+    got_d2, g = ops.gemm(a.cuda(), w.cuda(), act=act, dact_in=u.cuda(), aux_out=True, out_f32=True)
+    assert torch.equal(got_d2, got_d)
+    close(g, actf(u.float()).detach(), 5e-3, "act(u) from the dact epilogue")
+    # the CTA-pair flavoured kernels (M > 128, B operand MN-major as in the dgrad of the MLP) and the bf16 output
+    wt = w.t().contiguous()
+    got_d3, g3 = ops.gemm(a.cuda(), wt.cuda(), b_mn=True, act=act, dact_in=u.cuda(), aux_out=True)
+    close(got_d3, ref_d, 8e-3, "dact bf16, MN-major B")
+    close(g3, actf(u.float()).detach(), 5e-3, "act(u), MN-major B")
 
 
 @pytest.mark.parametrize("splits", [2, 5])
