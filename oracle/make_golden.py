@@ -7,6 +7,8 @@ Fixtures
   cnclip_tiny.pt   reference CNCLIP (ViT 2L/64w/patch 8 @32px + BERT 2L/64h, embed 32), fp32, dropout 0:
                    state_dict, inputs, forward outputs, symmetric-CE loss, gradients of every parameter
   cnclip_tiny_h80.pt  same with vision_head_width=80-style odd head dim (width 160, 2 heads of 80) — ViT-H head geometry
+  m2_tiny.pt       reference BEiT3 (multiway, 2 layers) + backbone_vl Encoder (1 layer) + ITC heads composed exactly as
+                   VLMo.infer_image / infer_text (vlmo_module.py:323-405): hiddens, both feature pairs, ITC loss, all gradients
   losses.pt        get_mil_nce_loss / get_l1_simi_matrix / moco_loss known answers incl. SURVEY.md §8c (1)
 """
 import os
@@ -151,8 +153,82 @@ def make_retrieval():
     print("retrieval.pt", out["square"]["recall"], out["multi_gt"]["metrics"])
 
 
+def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, patch=8, vocab=256, L=12, B=5, out_dim=32):
+    """M²-Encoder path with the UNMODIFIED reference classes. VLMo itself is a LightningModule whose constructor loads
+    tokenizers/timm (not importable here), so its infer_image / infer_text bodies (vlmo_module.py:323-405) are composed
+    here line by line from the same sub-modules and parameter names (backbone, backbone_vl, itc_*_proj, logit_*scale)."""
+    import copy
+
+    import numpy as np
+
+    m2 = ref_loader.load_m2()
+    torch.manual_seed(0)
+    args = m2.EncoderConfig(img_size=img, patch_size=patch, vocab_size=vocab, multiway=True, layernorm_embedding=False,
+                            normalize_output=True, no_output_layer=True, drop_path_rate=0, encoder_embed_dim=W,
+                            encoder_attention_heads=heads, encoder_layers=layers, encoder_ffn_embed_dim=4 * W,
+                            checkpoint_activations=False, max_text_len=L)
+    model = torch.nn.Module()
+    model.backbone = m2.BEiT3(args)
+    vl_args = copy.copy(args)
+    vl_args.encoder_layers = vl_layers
+    model.backbone_vl = m2.Encoder(vl_args)                       # vlmo_module.py:171-174
+    model.itc_text_proj = m2.heads.ITCHead(W, out_dim)            # :186-194
+    model.itc_image_proj = m2.heads.ITCHead(W, out_dim)
+    model.itc_vl_text_proj = m2.heads.ITCHead(W, out_dim)
+    model.itc_vl_image_proj = m2.heads.ITCHead(W, out_dim)
+    model.logit_scale = torch.nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
+    model.logit_vl_scale = torch.nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("bias") or "layer_norm" in n or "layernorm" in n or "_ln" in n or "token" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            if "embed_positions" in n or "itc_" in n:
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    model.train()
+    gen = torch.Generator().manual_seed(1234)
+    image = torch.randn(B, 3, img, img, generator=gen)
+    ids = synth_text(B, L, vocab, gen)
+    masks = (ids != 0).long()
+    # ---- infer_image (:385-398)
+    vffn = model.backbone(visual_tokens=image)["encoder_out"]
+    vl_v = model.backbone_vl(src_tokens=None, token_embeddings=vffn, multiway_split_position=-1)["encoder_out"]
+    img_f = model.itc_image_proj(vffn[:, 0])
+    img_f = img_f / img_f.norm(dim=-1, keepdim=True)
+    img_fv = model.itc_vl_image_proj(vl_v[:, 0])
+    img_fv = img_fv / img_fv.norm(dim=-1, keepdim=True)
+    # ---- infer_text (:333-355)
+    pad = 1 - masks
+    lffn = model.backbone(textual_tokens=ids, text_padding_position=pad)["encoder_out"]
+    vl_t = model.backbone_vl(src_tokens=None, token_embeddings=lffn, encoder_padding_mask=pad, multiway_split_position=-1)["encoder_out"]
+    txt_f = model.itc_text_proj(lffn[:, 0])
+    txt_f = txt_f / txt_f.norm(dim=-1, keepdim=True)
+    txt_fv = model.itc_vl_text_proj(vl_t[:, 0])
+    txt_fv = txt_fv / txt_fv.norm(dim=-1, keepdim=True)
+    # ---- similarity as m2_encoder.py:92-95, symmetric CE on both head pairs
+    labels = torch.arange(B)
+    lg = model.logit_scale.exp() * img_f @ txt_f.t()
+    lgv = model.logit_vl_scale.exp() * img_fv @ txt_fv.t()
+    loss = 0.5 * (F.cross_entropy(lg, labels) + F.cross_entropy(lg.t(), labels)) + 0.5 * (F.cross_entropy(lgv, labels) + F.cross_entropy(lgv.t(), labels))
+    loss.backward()
+    fx = {
+        "config": dict(W=W, heads=heads, layers=layers, vl_layers=vl_layers, img=img, patch=patch, vocab=vocab, L=L, out_dim=out_dim),
+        "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "image": image, "ids": ids, "masks": masks,
+        "image_hidden": vffn.detach(), "text_hidden": lffn.detach(),
+        "img_f": img_f.detach(), "txt_f": txt_f.detach(), "img_fv": img_fv.detach(), "txt_fv": txt_fv.detach(),
+        "logits": lg.detach(), "loss": loss.detach(),
+        "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None},
+    }
+    torch.save(fx, os.path.join(OUT, name))
+    print(name, "loss", float(loss.detach()), "params", sum(p.numel() for p in model.parameters()), "with grad", len(fx["grads"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--m2-only" in sys.argv:
+        make_m2()
+        sys.exit(0)
     if "--retrieval-only" in sys.argv:
         make_retrieval()
         sys.exit(0)
@@ -166,3 +242,4 @@ if __name__ == "__main__":
     make_cnclip("cnclip_tiny_h80.pt", h80, B=5, L=12, vocab_used=128)
     make_losses()
     make_retrieval()
+    make_m2()

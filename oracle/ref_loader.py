@@ -136,3 +136,59 @@ def build_cnclip(name_or_cfg, seed=0, dropout=0.0):
     with torch.no_grad():
         m.text_projection.normal_(0.0, cfg["text_hidden_size"] ** -0.5)
     return m
+
+
+def load_m2():
+    """Unmodified M²-Encoder (BEiT-3 multiway) reference modules from ``prj/M2_Encoder`` (SURVEY.md §8c recipe):
+    .BEiT3 (vlmo/torchscale/model/BEiT3.py), .Encoder / .EncoderLayer (architecture/encoder.py), .EncoderConfig
+    (architecture/config.py), .heads (vlmo/modules/heads.py). ``fairscale``, ``pytorch_lightning`` and ``timm`` are
+    not installed: they are replaced by identity stubs (checkpoint wrappers, rank_zero_info, drop_path at rate 0 —
+    none of them does arithmetic on the path). ``vlmo`` / ``vlmo.modules`` are pre-seeded as bare packages because
+    ``vlmo/modules/__init__.py`` would import the Lightning module (tokenizers, timm model zoo)."""
+    if "m2" in _loaded:
+        return _loaded["m2"]
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+    import torch
+
+    root = os.path.join(REF_ROOT, "prj", "M2_Encoder")
+
+    def stub(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    ident = lambda module, *a, **k: module  # noqa: E731
+    if "fairscale" not in sys.modules:
+        stub("fairscale")
+        stub("fairscale.nn", checkpoint_wrapper=ident, wrap=ident)
+    if "pytorch_lightning" not in sys.modules:
+        stub("pytorch_lightning")
+        stub("pytorch_lightning.utilities")
+        stub("pytorch_lightning.utilities.distributed", rank_zero_info=lambda *a, **k: None)
+    if "timm" not in sys.modules:
+
+        def drop_path(x, drop_prob=0.0, training=False):
+            if drop_prob != 0.0 and training:
+                raise NotImplementedError("stub: drop_path only at rate 0")
+            return x
+
+        stub("timm")
+        stub("timm.models")
+        stub("timm.models.layers", drop_path=drop_path, trunc_normal_=torch.nn.init.trunc_normal_)
+    _pkg("vlmo", root + "/vlmo")
+    _pkg("vlmo.modules", root + "/vlmo/modules")
+    ns = types.SimpleNamespace()
+    ns.BEiT3 = importlib.import_module("vlmo.torchscale.model.BEiT3").BEiT3
+    enc = importlib.import_module("vlmo.torchscale.architecture.encoder")
+    ns.Encoder, ns.EncoderLayer = enc.Encoder, enc.EncoderLayer
+    ns.EncoderConfig = importlib.import_module("vlmo.torchscale.architecture.config").EncoderConfig
+    ns.heads = importlib.import_module("vlmo.modules.heads")
+    ns.multiway = importlib.import_module("vlmo.torchscale.component.multiway_network")
+    _loaded["m2"] = ns
+    return ns

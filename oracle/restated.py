@@ -250,3 +250,98 @@ def sym_recall(sim, t2v, v2t):
 
 def to_dtype(sd, dtype):
     return {k: (v.to(dtype) if torch.is_floating_point(v) else v) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# M²-Encoder (BEiT-3 multiway transformer)  — prj/M2_Encoder/vlmo  
+# ----------------------------------------------------------------------------------------------------------------
+def m2_attention(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
+    """MultiheadAttention.forward, vlmo/torchscale/component/multihead_attention.py:66-154 with the multiway expert
+    `way` ("A" vision / "B" language, multiway_network.py:33-45): q scaled by hd^-0.5 BEFORE q·k^T (:95), key padding
+    → -inf (:129-135), softmax in fp32 (:141), sub-LN `inner_attn_ln` on the merged heads (:148-149), out_proj (:151)."""
+    B, L, W = x.shape
+    hd = W // heads
+    lin = lambda n, t: t @ sd[f"{pfx}{n}.{way}.weight"].t() + sd[f"{pfx}{n}.{way}.bias"]  # noqa: E731
+    q = (lin("q_proj", x) * hd ** -0.5).view(B, L, heads, hd).transpose(1, 2)
+    k = lin("k_proj", x).view(B, L, heads, hd).transpose(1, 2)
+    v = lin("v_proj", x).view(B, L, heads, hd).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if key_pad is not None:
+        s = s.masked_fill(key_pad.bool()[:, None, None, :], float("-inf"))
+    a = (torch.softmax(s.float(), dim=-1).to(s.dtype) @ v).transpose(1, 2).reshape(B, L, W)
+    a = layer_norm(a, sd[f"{pfx}inner_attn_ln.{way}.weight"], sd[f"{pfx}inner_attn_ln.{way}.bias"], eps)
+    return lin("out_proj", a)
+
+
+def m2_ffn(sd, pfx, x, way, eps=1e-5):
+    """FeedForwardNetwork.forward, vlmo/torchscale/component/feedforward_network.py:117-128: fc2(ffn_layernorm(gelu(fc1 x)))
+    (activation "gelu" = exact erf GELU, :97-103; sub-LN over the ffn width)."""
+    u = x @ sd[f"{pfx}{way}.fc1.weight"].t() + sd[f"{pfx}{way}.fc1.bias"]
+    g = layer_norm(F.gelu(u), sd[f"{pfx}{way}.ffn_layernorm.weight"], sd[f"{pfx}{way}.ffn_layernorm.bias"], eps)
+    return g @ sd[f"{pfx}{way}.fc2.weight"].t() + sd[f"{pfx}{way}.fc2.bias"]
+
+
+def m2_encoder_layer(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
+    """EncoderLayer.forward, vlmo/torchscale/architecture/encoder.py:113-168 with normalize_before=True, subln=True,
+    alpha = 1 (no deepnorm), dropout / drop_path 0, no MoE."""
+    h = layer_norm(x, sd[f"{pfx}self_attn_layer_norm.{way}.weight"], sd[f"{pfx}self_attn_layer_norm.{way}.bias"], eps)
+    x = x + m2_attention(sd, pfx + "self_attn.", h, heads, way, key_pad, eps)
+    h = layer_norm(x, sd[f"{pfx}final_layer_norm.{way}.weight"], sd[f"{pfx}final_layer_norm.{way}.bias"], eps)
+    return x + m2_ffn(sd, pfx + "ffn.", h, way, eps)
+
+
+def m2_encoder(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
+    """Encoder.forward, architecture/encoder.py:388-482, from token embeddings `x` that already carry positions:
+    zero the padded rows (:440), the layers, final `layer_norm` (:469-470; normalize_output=True)."""
+    if key_pad is not None:
+        x = x * (1 - key_pad.unsqueeze(-1).to(x.dtype))
+    n_layers = 1 + max(int(k[len(pfx) :].split(".")[1]) for k in sd if k.startswith(pfx + "layers."))
+    for i in range(n_layers):
+        x = m2_encoder_layer(sd, f"{pfx}layers.{i}.", x, heads, way, key_pad, eps)
+    return layer_norm(x, sd[f"{pfx}layer_norm.{way}.weight"], sd[f"{pfx}layer_norm.{way}.bias"], eps)
+
+
+def m2_vision_embed(sd, pfx, image):
+    """VisionEmbedding.forward, vlmo/torchscale/component/embedding.py:67-83 (conv with bias, CLS prepended; no mask
+    positions) + PositionalEmbedding expert A starting at position 2 (embedding.py:93-110, encoder.py:353-363)."""
+    w = sd[pfx + "vision_embed.proj.weight"]
+    width, p = w.shape[0], w.shape[-1]
+    x = patchify(image, p) @ w.reshape(width, -1).t() + sd[pfx + "vision_embed.proj.bias"]
+    x = torch.cat([sd[pfx + "vision_embed.cls_token"].expand(x.shape[0], 1, width), x], dim=1)
+    L = x.shape[1]
+    return x + sd[pfx + "encoder.embed_positions.A.weight"][2 : L + 2]
+
+
+def m2_text_embed(sd, pfx, ids):
+    """TextEmbedding lookup (embedding.py:86-90) + PositionalEmbedding expert B, positions 2..L+1."""
+    L = ids.shape[1]
+    return sd[pfx + "text_embed.weight"][ids] + sd[pfx + "encoder.embed_positions.B.weight"][2 : L + 2]
+
+
+def m2_infer_image(sd, image, heads):
+    """VLMo.infer_image, vlmo/modules/vlmo_module.py:364-405 (the caller passes the already inception-normalised
+    tensor, :385): backbone with expert A, backbone_vl with expert A (split −1), ITC heads on the CLS rows, L2-norm."""
+    h = m2_encoder(sd, "backbone.encoder.", m2_vision_embed(sd, "backbone.", image), heads, "A")
+    hv = m2_encoder(sd, "backbone_vl.", h, heads, "A")
+    f = h[:, 0] @ sd["itc_image_proj.fc.weight"].t()
+    fv = hv[:, 0] @ sd["itc_vl_image_proj.fc.weight"].t()
+    return h, f / f.norm(dim=-1, keepdim=True), fv / fv.norm(dim=-1, keepdim=True)
+
+
+def m2_infer_text(sd, ids, masks, heads):
+    """VLMo.infer_text, vlmo_module.py:323-362: backbone with expert B and key padding = 1 − text_masks; backbone_vl
+    with expert A (split −1, :343) on the language hiddens; ITC heads on CLS, L2-norm."""
+    pad = 1 - masks
+    h = m2_encoder(sd, "backbone.encoder.", m2_text_embed(sd, "backbone.", ids), heads, "B", pad)
+    hv = m2_encoder(sd, "backbone_vl.", h, heads, "A", pad)
+    f = h[:, 0] @ sd["itc_text_proj.fc.weight"].t()
+    fv = hv[:, 0] @ sd["itc_vl_text_proj.fc.weight"].t()
+    return h, f / f.norm(dim=-1, keepdim=True), fv / fv.norm(dim=-1, keepdim=True)
+
+
+def m2_itc_loss(sd, img_f, txt_f, img_fv, txt_fv):
+    """Symmetric InfoNCE on both ITC head pairs with their own temperatures: logits = exp(logit_scale)·I·Tᵀ as in
+    prj/M2_Encoder/m2_encoder.py:92-95 (`logit_vl_scale` for the VL-layer heads, vlmo_module.py:193-194)."""
+    l1 = symmetric_info_nce(sd["logit_scale"].exp() * img_f @ txt_f.t())
+    l2 = symmetric_info_nce(sd["logit_vl_scale"].exp() * img_fv @ txt_fv.t())
+    return l1 + l2

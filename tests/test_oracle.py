@@ -150,3 +150,29 @@ def test_restated_retrieval_metrics_match_live_reference():
     v2t = [sorted(set(int(i) for i in rng.integers(0, 20, size=3))) for _ in range(6)]
     a, b = restated.sym_recall(x, t2v, v2t), fn._cal_sym_recall(x, t2v, v2t)
     assert all(abs(a[k] - float(b[k])) < 1e-12 for k in b)
+
+
+def test_restated_m2_encoder_matches_golden_forward_backward(golden_dir):
+    """M²-Encoder (BEiT-3 multiway) restatement vs the unmodified reference classes (oracle/make_golden.py::make_m2)."""
+    fx = _load(golden_dir, "m2_tiny.pt")
+    heads = fx["config"]["heads"]
+    sd = {k: v.clone().requires_grad_(torch.is_floating_point(v)) for k, v in fx["state_dict"].items()}
+    h_i, img_f, img_fv = restated.m2_infer_image(sd, fx["image"], heads)
+    h_t, txt_f, txt_fv = restated.m2_infer_text(sd, fx["ids"], fx["masks"], heads)
+    torch.testing.assert_close(h_i, fx["image_hidden"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(h_t, fx["text_hidden"], rtol=1e-4, atol=2e-5)
+    for got, key in [(img_f, "img_f"), (txt_f, "txt_f"), (img_fv, "img_fv"), (txt_fv, "txt_fv")]:
+        torch.testing.assert_close(got, fx[key], rtol=1e-4, atol=1e-5)
+    loss = restated.m2_itc_loss(sd, img_f, txt_f, img_fv, txt_fv)
+    torch.testing.assert_close(loss, fx["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    assert len(fx["grads"]) > 100
+    for n, g in fx["grads"].items():
+        got = sd[n].grad
+        assert got is not None, n
+        denom = g.abs().max().clamp_min(1e-4)  # k_proj.bias grads are analytically 0 (softmax shift invariance)
+        assert float((got - g).abs().max() / denom) < 3e-4, n
+    # parameters the reference leaves without gradient on this path stay without gradient in the restatement too
+    for n, v in sd.items():
+        if torch.is_floating_point(v) and n not in fx["grads"]:
+            assert v.grad is None or float(v.grad.abs().max()) == 0.0, n

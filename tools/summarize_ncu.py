@@ -1,0 +1,75 @@
+"""Turns the ncu outputs of tools/evidence*.sh into the markdown summaries committed under profiles/.
+
+  python tools/summarize_ncu.py launches gpurun_out/r01b_launches.csv   > profiles/r01b_launches_summary.md
+  python tools/summarize_ncu.py full     gpurun_out/r01b_kernels_raw.csv > profiles/r01b_kernels_ncu_summary.md
+"""
+import collections
+import csv
+import re
+import sys
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    tot = collections.defaultdict(lambda: [0, 0.0])
+    n = 0
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
+        name = re.sub(r"^void ", "", row["Kernel Name"])
+        name = re.sub(r"\(.*", "", name)
+        tot[name][0] += 1
+        tot[name][1] += v
+        n += 1
+    T = sum(v[1] for v in tot.values())
+    ours = sum(v[1] for k, v in tot.items() if "b200mm::" in k)
+    gemm = sum(v[1] for k, v in tot.items() if "gemm_tcgen05" in k or "splitk" in k)
+    print(f"# ncu launch list `{path}`: {n} launches, {T / 1e3:.1f} ms of kernel time (cold-cache, serialised replays: use the SHARES)\n")
+    print(f"b200mm kernels: {100 * ours / T:.2f} % of kernel time; tcgen05 GEMM (+ split-K reduce): {100 * gemm / T:.2f} %\n")
+    print("| kernel | launches | total ms | share % |\n|---|---|---|---|")
+    for k, (c, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        if us / T < 2e-4:
+            continue
+        print(f"| `{k[:110]}` | {c} | {us / 1e3:.2f} | {100 * us / T:.2f} |")
+
+
+def full(path):
+    r = csv.reader(open(path))
+    hdr = next(r)
+    next(r)
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def find(sub):
+        for h, i in col.items():
+            if h.endswith(sub):
+                return i
+        return None
+
+    want = [("time us", "gpu__time_duration.sum"), ("dram rd GB", "dram__bytes_read.sum"), ("dram wr GB", "dram__bytes_write.sum"),
+            ("dram TB/s (rd+wr)/t", None), ("tensor pipe %", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"),
+            ("issue active %", "sm__inst_issued.avg.pct_of_peak_sustained_active"), ("warps active %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+            ("regs", "launch__registers_per_thread"), ("warp inst (M)", "smsp__inst_executed.sum"), ("XU pipe %", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active")]
+    idx = [(n, find(m) if m else -1) for n, m in want]
+    print(f"# ncu --set full --clock-control none, one launch per hot kernel (tools/prof_kernels.py) — `{path}`\n")
+    print("| kernel | grid | " + " | ".join(n for n, _ in idx) + " |\n|---|---|" + "---|" * len(idx))
+    for row in r:
+        name = re.sub(r"\(.*", "", re.sub(r"^void ", "", row[col["Kernel Name"]]))[:70]
+        vals = []
+        for n, i in idx:
+            if i == -1:
+                t = float(row[find("gpu__time_duration.sum")].replace(",", ""))
+                b = float(row[find("dram__bytes_read.sum")].replace(",", "")) + float(row[find("dram__bytes_write.sum")].replace(",", ""))
+                vals.append(f"{b / t * 1e3:.2f}")  # GB per us = 1e3 TB/s
+                continue
+            if i is None or row[i] == "":
+                vals.append("n/a")
+                continue
+            v = float(row[i].replace(",", ""))
+            vals.append(f"{v / 1e6:.1f}" if n.startswith("warp inst") else f"{v:.3g}" if v < 100 else f"{v:.1f}")
+        print(f"| `{name}` | {row[col['Grid Size']]} | " + " | ".join(vals) + " |")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
