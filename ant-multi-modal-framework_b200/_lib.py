@@ -52,6 +52,9 @@ SIGNATURES = {
     "b200mm_contrast_rank": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P]),
     "b200mm_masked_mean_fwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "b200mm_masked_mean_bwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "b200mm_act_layernorm_fwd": (c_int32, [_P, c_int32, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P]),
+    "b200mm_act_layernorm_bwd": (c_int32, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
+    "b200mm_mask_rows": (c_int32, [_P, _P, _P, c_int64, c_int32, _P]),
     "b200mm_act_fwd": (c_int32, [_P, _P, c_int64, c_int32, _P]),
     "b200mm_rowsum_periodic": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P]),
     "b200mm_scatter_add_rows": (c_int32, [_P, _I64P, _P, c_int64, c_int32, c_int64, c_int64, _P]),

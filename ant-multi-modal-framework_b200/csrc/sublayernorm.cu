@@ -230,16 +230,6 @@ __global__ void __launch_bounds__(256) mask_rows_kernel(const uint4* __restrict_
   }
 }
 
-template <int ACT, bool FWD, typename... Args>
-static int launch_sub_ln(int32_t W, int grid, cudaStream_t stream, Args... args) {
-  const int v128 = static_cast<int>(ceil_div(W, 128 * 8));
-#define B200MM_SL(V, T)                                                             \
-  if (FWD) act_ln_fwd_kernel<V, T, ACT><<<grid, T, 0, stream>>>(args...);           \
-  else act_ln_bwd_kernel<V, T, ACT><<<grid, T, 0, stream>>>(args...);
-  return 0;
-#undef B200MM_SL
-}
-
 }  // namespace b200mm
 
 using namespace b200mm;
@@ -258,12 +248,9 @@ int sub_ln_fwd(const __nv_bfloat16* u, const __nv_bfloat16* w, const __nv_bfloat
     case 2: act_ln_fwd_kernel<2, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
     case 3: act_ln_fwd_kernel<3, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
     case 4: act_ln_fwd_kernel<4, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
-    default: {
-      const int v2 = static_cast<int>(ceil_div(W, 2048));  // 256 threads
-      if (v2 <= 4) act_ln_fwd_kernel<4, 256, ACT><<<grid, 256, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps);
-      else if (v2 <= 8) act_ln_fwd_kernel<8, 256, ACT><<<grid, 256, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps);
-      else { set_last_error("act_layernorm_fwd: width %d not supported (max 16384)", W); return B200MM_ERR_SHAPE; }
-    }
+    default:
+      if (W <= 8192) act_ln_fwd_kernel<4, 256, ACT><<<grid, 256, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps);
+      else { set_last_error("act_layernorm_fwd: width %d not supported (max 8192)", W); return B200MM_ERR_SHAPE; }
   }
   return check_launch("act_ln_fwd_kernel");
 }
@@ -273,19 +260,12 @@ int sub_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* u, const float* mea
                float* dw, float* db, int64_t rows, int32_t W, cudaStream_t st) {
   // each CTA ends with 2·W atomics: keep the CTA count at a few per SM
   const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(sm_count()) * 4));
-  const int v = static_cast<int>(ceil_div(W, 1024));
-  switch (v) {
-    case 1: act_ln_bwd_kernel<1, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W); break;
-    case 2: act_ln_bwd_kernel<2, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W); break;
-    case 3: act_ln_bwd_kernel<3, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W); break;
-    case 4: act_ln_bwd_kernel<4, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W); break;
-    default: {
-      const int v2 = static_cast<int>(ceil_div(W, 2048));
-      if (v2 <= 4) act_ln_bwd_kernel<4, 256, ACT><<<grid, 256, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
-      else if (v2 <= 8) act_ln_bwd_kernel<8, 256, ACT><<<grid, 256, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
-      else { set_last_error("act_layernorm_bwd: width %d not supported (max 16384)", W); return B200MM_ERR_SHAPE; }
-    }
-  }
+  // register budget: 2 accumulators + xhat + dy*w per column held by the thread -> at most 32 columns per thread below 8192
+  if (W <= 1024) act_ln_bwd_kernel<1, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
+  else if (W <= 2048) act_ln_bwd_kernel<2, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
+  else if (W <= 4096) act_ln_bwd_kernel<2, 256, ACT><<<grid, 256, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
+  else if (W <= 8192) act_ln_bwd_kernel<4, 256, ACT><<<grid, 256, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
+  else { set_last_error("act_layernorm_bwd: width %d not supported (max 8192)", W); return B200MM_ERR_SHAPE; }
   return check_launch("act_ln_bwd_kernel");
 }
 

@@ -323,3 +323,238 @@ class RowNormFn(Function):
     def backward(ctx, dy):
         x, inv = ctx.saved_tensors
         return ops.rownorm_bwd(dy.float().contiguous(), x, inv)
+
+
+# ======================================================================================================================
+# M²-Encoder (BEiT-3 multiway) encoder layer: pre-LN + sub-LN — prj/M2_Encoder/vlmo/torchscale/architecture/encoder.py:113-168,
+# attention component/multihead_attention.py:66-154, FFN component/feedforward_network.py:117-128
+# ======================================================================================================================
+def _m2_layer_forward(x, p, key_bias, B, L, H, eps):
+    (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b) = p
+    W = x.shape[1]
+    h1, _, mean1, rstd1 = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
+    qkv = ops.gemm(h1, qkv_w, bias=qkv_b)
+    del h1
+    # the reference scales q by hd^-0.5 before q·k^T (multihead_attention.py:95); the kernel applies the same factor to the scores
+    a, lse = ops.attention_fwd(qkv, B, L, H, W // H, key_bias=key_bias)
+    a_n, _, mean_i, rstd_i = ops.layernorm_fwd(a, iln_w, iln_b, eps)  # inner_attn_ln on the merged heads (:148-149)
+    x_mid = ops.gemm(a_n, o_w, bias=o_b, residual=x)
+    del a_n
+    h2, _, mean2, rstd2 = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+    u = ops.gemm(h2, fc1_w, bias=fc1_b)
+    del h2
+    g_n, mean_f, rstd_f = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)  # ffn_layernorm(gelu(u)) in one pass
+    y = ops.gemm(g_n, fc2_w, bias=fc2_b, residual=x_mid)
+    return y, (mean1, rstd1, qkv, a, lse, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f)
+
+
+class M2EncoderLayerFn(Function):
+    """One multiway expert (A or B) of an EncoderLayer applied to every token (split_position −1 / 0)."""
+
+    @staticmethod
+    def forward(ctx, x, ln1_w, ln1_b, q_w, q_b, k_w, k_b, v_w, v_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b,
+                fc2_w, fc2_b, key_bias, B, L, H, eps, checkpoint):
+        qkv_w = torch.cat([q_w, k_w, v_w], dim=0)
+        qkv_b = torch.cat([q_b, k_b, v_b], dim=0)
+        p = (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b)
+        y, saved = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+        ctx.meta = (B, L, H, eps, checkpoint, key_bias is not None)
+        kb = (key_bias,) if key_bias is not None else ()
+        if checkpoint:
+            ctx.save_for_backward(x, *p, *kb)
+        else:
+            ctx.save_for_backward(x, *p, *kb, *saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, L, H, eps, checkpoint, has_kb = ctx.meta
+        t = ctx.saved_tensors
+        x, p = t[0], t[1:17]
+        key_bias = t[17] if has_kb else None
+        rest = t[17 + int(has_kb):]
+        (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b) = p
+        if checkpoint:
+            _, rest = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+        mean1, rstd1, qkv, a, lse, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f = rest
+        W = x.shape[1]
+        F_ = fc1_w.shape[0]
+        dy = dy.contiguous()
+        # ln1 w,b | qkv_b | iln w,b | o_b | ln2 w,b | fc1_b | fln w,b | fc2_b
+        vg = _VecGrads(x.device, [W, W, 3 * W, W, W, W, W, W, F_, F_, F_, W])
+        # ---- FFN branch: fc2(ffn_ln(gelu(fc1 h2)))
+        g_n, _, _ = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)  # recomputed, never kept
+        d_fc2_w = _wgrad(dy, g_n)
+        del g_n
+        ops.rowsum_periodic(dy, vg[11])
+        dg_n = ops.gemm(dy, fc2_w, b_mn=True)
+        du = ops.act_layernorm_bwd(dg_n, u, ACT_GELU_ERF, mean_f, rstd_f, fln_w, vg[9], vg[10])  # through sub-LN and gelu' at once
+        del dg_n
+        h2, _, _, _ = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+        d_fc1_w = _wgrad(du, h2)
+        del h2
+        ops.rowsum_periodic(du, vg[8])
+        dh2 = ops.gemm(du, fc1_w, b_mn=True)
+        del du
+        dx_mid = ops.layernorm_bwd(dh2, x_mid, mean2, rstd2, ln2_w, vg[6], vg[7], dadd=dy)
+        del dh2
+        # ---- attention branch: out_proj(inner_ln(attn(qkv(ln1 x))))
+        a_n, _, _, _ = ops.layernorm_fwd(a, iln_w, iln_b, eps)
+        d_o_w = _wgrad(dx_mid, a_n)
+        del a_n
+        ops.rowsum_periodic(dx_mid, vg[5])
+        da_n = ops.gemm(dx_mid, o_w, b_mn=True)
+        da = ops.layernorm_bwd(da_n, a, mean_i, rstd_i, iln_w, vg[3], vg[4])
+        del da_n
+        dqkv = ops.attention_bwd(qkv, a, da, lse, B, L, H, W // H, key_bias=key_bias)
+        del da
+        h1, _, _, _ = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
+        d_qkv_w = _wgrad(dqkv, h1)
+        del h1
+        ops.rowsum_periodic(dqkv, vg[2])
+        dh1 = ops.gemm(dqkv, qkv_w, b_mn=True)
+        del dqkv
+        dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, vg[0], vg[1], dadd=dx_mid)
+        d_ln1_w, d_ln1_b, d_qkv_b, d_iln_w, d_iln_b, d_o_b, d_ln2_w, d_ln2_b, d_fc1_b, d_fln_w, d_fln_b, d_fc2_b = vg.finish()
+        dq_w, dk_w, dv_w = d_qkv_w[:W], d_qkv_w[W: 2 * W], d_qkv_w[2 * W:]
+        dq_b, dk_b, dv_b = d_qkv_b[:W], d_qkv_b[W: 2 * W], d_qkv_b[2 * W:]
+        return (dx, d_ln1_w, d_ln1_b, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_iln_w, d_iln_b, d_o_w, d_o_b, d_ln2_w, d_ln2_b, d_fc1_w, d_fc1_b,
+                d_fln_w, d_fln_b, d_fc2_w, d_fc2_b, None, None, None, None, None, None)
+
+
+class LayerNormFn(Function):
+    """Plain LayerNorm over all rows (Encoder.layer_norm, architecture/encoder.py:469-470)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, _, mean, rstd = ops.layernorm_fwd(x, w, b, eps)
+        ctx.save_for_backward(x, mean, rstd, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, w = ctx.saved_tensors
+        W = x.shape[1]
+        vg = _VecGrads(x.device, [W, W])
+        dx = ops.layernorm_bwd(dy.contiguous(), x, mean, rstd, w, vg[0], vg[1])
+        dw, db = vg.finish()
+        return dx, dw, db, None
+
+
+class MaskRowsFn(Function):
+    """x * (1 − padding) on token rows (Encoder.forward, architecture/encoder.py:440); the gradient is masked the same way."""
+
+    @staticmethod
+    def forward(ctx, x, drop):
+        ctx.save_for_backward(drop)
+        return ops.mask_rows(x, drop)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (drop,) = ctx.saved_tensors
+        return ops.mask_rows(dy.contiguous(), drop), None
+
+
+class ClsLinearFn(Function):
+    """ITCHead on the CLS rows: x[:, 0] @ weight^T, weight [E, W] bias-free (vlmo/modules/heads.py:17-24, vlmo_module.py:346,389)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, B, L):
+        W = x.shape[1]
+        xc = x.view(B, L, W)[:, 0, :].contiguous()
+        ctx.save_for_backward(xc, weight)
+        ctx.meta = (B, L)
+        return ops.gemm(xc, weight)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, weight = ctx.saved_tensors
+        B, L = ctx.meta
+        dout = dout.contiguous()
+        dxc = ops.gemm(dout, weight, b_mn=True)  # [B, W] = dout [B, E] · weight [E, W]
+        d_w = ops.gemm(dout, xc, a_mn=True, b_mn=True)  # [E, W] = dout^T xc
+        dx = torch.zeros((B * L, xc.shape[1]), device=xc.device, dtype=BF16)
+        dx.view(B, L, -1)[:, 0, :] = dxc
+        return dx, d_w, None, None
+
+
+class M2VisionEmbedFn(Function):
+    """VisionEmbedding (conv patch-embed with bias, CLS prepended; component/embedding.py:67-83) + positional expert A from
+    position 2 (embedding.py:93-110). `pos` is the [L, W] slice embed_positions.A.weight[2:L+2]."""
+
+    @staticmethod
+    def forward(ctx, image, conv_w, conv_b, cls, pos):
+        Bn, C, Hh, Ww = image.shape
+        width, _, p, _ = conv_w.shape
+        K = C * p * p
+        Kp = (K + 63) // 64 * 64
+        L = (Hh // p) * (Ww // p) + 1
+        if pos.shape[0] != L:
+            raise ops._lib.B200mmError(f"embed_positions.A gives {pos.shape[0]} rows, image gives {L} tokens")
+        patches = ops.im2row(image, p, Kp)  # one zero row per image for the CLS slot
+        w2d = torch.zeros((width, Kp), device=image.device, dtype=BF16)
+        w2d[:, :K] = conv_w.reshape(width, K)
+        raw = ops.gemm(patches, w2d)
+        del patches
+        add0 = pos.clone()
+        add0[1:] += conv_b  # the conv bias belongs to the patch rows only ([L, W] parameter-sized op)
+        one = torch.ones(width, device=image.device, dtype=BF16)
+        zero = torch.zeros(width, device=image.device, dtype=BF16)
+        _, s, _, _ = ops.layernorm_fwd(raw, one, zero, 1e-5, add0=add0, add1=cls.reshape(-1), add_period=L, want_sum=True)
+        ctx.save_for_backward(image)
+        ctx.meta = (p, K, Kp, L, tuple(conv_w.shape), tuple(cls.shape))
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        (image,) = ctx.saved_tensors
+        p, K, Kp, L, wshape, cshape = ctx.meta
+        ds = ds.contiguous()
+        W = ds.shape[1]
+        vg = _VecGrads(ds.device, [L * W])
+        ops.rowsum_periodic(ds, vg[0].view(L, W), period=L)
+        patches = ops.im2row(image, p, Kp)
+        d_w2d = _wgrad(ds, patches)
+        d_conv = d_w2d[:, :K].reshape(wshape)
+        dadd32 = vg[0].view(L, W)
+        d_bias = dadd32[1:].sum(0).to(BF16)  # [L, W] parameter-sized reduction
+        (d_add,) = vg.finish()
+        d_add = d_add.view(L, W)
+        return None, d_conv, d_bias, d_add[0].reshape(cshape).clone(), d_add
+
+
+class M2TextEmbedFn(Function):
+    """TextEmbedding lookup + positional expert B from position 2, padded rows zeroed (BEiT3.forward model/BEiT3.py:64-67,
+    Encoder.forward_embedding architecture/encoder.py:353-363 and :440). `pos` = embed_positions.B.weight[2:L+2]."""
+
+    @staticmethod
+    def forward(ctx, word, ids, pos, drop):
+        Bn, L = ids.shape
+        W = word.shape[1]
+        flat = ids.reshape(-1).contiguous()
+        ztype = torch.zeros((1, W), device=word.device, dtype=BF16)
+        zids = torch.zeros_like(flat)
+        one = torch.ones(W, device=word.device, dtype=BF16)
+        zero = torch.zeros(W, device=word.device, dtype=BF16)
+        _, s, _, _ = ops.embed_layernorm_fwd(word, flat, pos.contiguous(), L, ztype, zids, one, zero, 1e-5)
+        if drop is not None:
+            s = ops.mask_rows(s, drop, inplace=True)
+        ctx.save_for_backward(flat, drop)
+        ctx.meta = (L, word.shape[0])
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        flat, drop = ctx.saved_tensors
+        L, n_word = ctx.meta
+        ds = ds.contiguous()
+        if drop is not None:
+            ds = ops.mask_rows(ds, drop)
+        W = ds.shape[1]
+        vg = _VecGrads(ds.device, [L * W])
+        ops.rowsum_periodic(ds, vg[0].view(L, W), period=L)
+        acc = torch.zeros((n_word, W), device=ds.device, dtype=torch.float32)
+        ops.scatter_add_rows(ds, flat, acc)
+        d_word = ops.cast_f32_bf16(acc)
+        (d_pos,) = vg.finish()
+        return d_word, None, d_pos.view(L, W), None

@@ -162,6 +162,51 @@ def layernorm_bwd(dy, x, mean, rstd, w, dw32, db32, dadd=None):
     return dx
 
 
+def act_layernorm_fwd(u, act, w, b, eps):
+    """y = LN(act(u)) * w + b for rows of any width (sub-LN of the M2-Encoder blocks); returns (y, mean, rstd)."""
+    lib = _lib.load()
+    _req(u, "u", BF16, 2)
+    if not u.is_contiguous():
+        raise _lib.B200mmError("b200mm.act_layernorm_fwd: u must be contiguous")
+    rows, W = u.shape
+    y = torch.empty_like(u)
+    mean = torch.empty(rows, device=u.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=u.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_act_layernorm_fwd(_ptr(u), act, _ptr(_req(w, "w", BF16, 1)), _ptr(_req(b, "b", BF16, 1)), _ptr(y), _ptr(mean),
+                                            _ptr(rstd), rows, W, eps, _stream()), "b200mm_act_layernorm_fwd")
+    _count(1)
+    return y, mean, rstd
+
+
+def act_layernorm_bwd(dy, u, act, mean, rstd, w, dw32, db32):
+    """du = LN'(dy) * act'(u) (act(u) recomputed inside); dw32/db32 (f32 [W]) are accumulated into."""
+    lib = _lib.load()
+    _req(dy, "dy", BF16, 2)
+    _req(u, "u", BF16, 2)
+    if not (dy.is_contiguous() and u.is_contiguous()):
+        raise _lib.B200mmError("b200mm.act_layernorm_bwd: dy and u must be contiguous")
+    rows, W = dy.shape
+    du = torch.empty_like(dy)
+    _lib.check(lib.b200mm_act_layernorm_bwd(_ptr(dy), _ptr(u), act, _ptr(mean), _ptr(rstd), _ptr(w), _ptr(du),
+                                            _ptr(_req(dw32, "dw", torch.float32)), _ptr(_req(db32, "db", torch.float32)), rows, W, _stream()),
+               "b200mm_act_layernorm_bwd")
+    _count(1)
+    return du
+
+
+def mask_rows(x, drop, inplace=False):
+    """y[r, :] = 0 where drop[r] (uint8 [rows]) else x[r, :]."""
+    lib = _lib.load()
+    _req(x, "x", BF16, 2)
+    _req(drop, "drop", torch.uint8, 1)
+    if not x.is_contiguous():
+        raise _lib.B200mmError("b200mm.mask_rows: x must be contiguous")
+    y = x if inplace else torch.empty_like(x)
+    _lib.check(lib.b200mm_mask_rows(_ptr(x), _ptr(drop), _ptr(y), x.shape[0], x.shape[1], _stream()), "b200mm_mask_rows")
+    _count(1)
+    return y
+
+
 def embed_layernorm_fwd(word, ids, pos, L, type_table, type_ids, w, b, eps):
     lib = _lib.load()
     _req(word, "word", BF16, 2)

@@ -157,6 +157,18 @@ int b200mm_contrast_rank(const void* a, int64_t lda, const void* b, int64_t ldb,
  * inv_count[r] = 1/#valid (f32, consumed by the backward: dx[r,p,:] = valid * inv_count[r] * dy[r,:]). */
 int b200mm_masked_mean_fwd(const void* x, const uint8_t* pad, void* y, float* inv_count, int64_t R, int32_t P, int32_t W, void* stream);
 int b200mm_masked_mean_bwd(const void* dy, const uint8_t* pad, const float* inv_count, void* dx, int64_t R, int32_t P, int32_t W, void* stream);
+/* Sub-LayerNorm of the M2-Encoder (BEiT-3 multiway) blocks, fused with the activation in front of it; any row width W % 8 == 0
+ * up to 8192 (the FFN sub-LN spans the 4W hidden). Replaces `ffn_layernorm(gelu(fc1 x))`
+ * (prj/M2_Encoder/vlmo/torchscale/component/feedforward_network.py:117-128) and, with act = B200MM_ACT_NONE, `inner_attn_ln`
+ * (vlmo/torchscale/component/multihead_attention.py:148-149).
+ *   fwd: y = LN(act(u))*w + b, mean/rstd [rows] f32 saved;  bwd: du = LN'(dy)*act'(u) with act(u) recomputed, dw/db (f32 [W]) accumulated. */
+int b200mm_act_layernorm_fwd(const void* u, int32_t act, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows,
+                             int32_t W, float eps, void* stream);
+int b200mm_act_layernorm_bwd(const void* dy, const void* u, int32_t act, const float* mean, const float* rstd, const void* w, void* du,
+                             float* dw, float* db, int64_t rows, int32_t W, void* stream);
+/* y[r,:] = drop[r] ? 0 : x[r,:]  (bf16 [rows, W], drop = bytes): Encoder.forward zeroes the padded token rows,
+ * prj/M2_Encoder/vlmo/torchscale/architecture/encoder.py:440; the same call masks the gradient in backward. y may alias x. */
+int b200mm_mask_rows(const void* x, const uint8_t* drop, void* y, int64_t rows, int32_t W, void* stream);
 /* y = act(x), bf16, n % 8 == 0 (activation recompute in backward: QuickGELU clip/model.py:222-224, erf-GELU modeling_bert.py:31-37) */
 int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream);
 /* out[(row % period), :] += in[row, :]  (f32 atomics, caller zero-fills): period 1 = bias gradient of nn.Linear,

@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE — torch (CPU) stand-ins for the b200mm.ops kernel wrappers, used ONLY by the `not gpu` host-logic
+tests to run the autograd glue of b200mm.functional / b200mm.modules (saved-tensor order, gradient routing, parameter
+naming, masking) without a GPU. They follow the documented contract of each C-ABI entry point (include/b200mm.h) in fp32
+and round to bf16 where the kernels do. Never imported by the package: the product path has no CPU route.
+"""
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF = torch.bfloat16
+ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF = 0, 1, 2
+
+
+def _act(act, x):
+    return x * torch.sigmoid(1.702 * x) if act == ACT_QUICKGELU else (F.gelu(x) if act == ACT_GELU_ERF else x)
+
+
+def _dact(act, x):
+    with torch.enable_grad():  # called from inside autograd backward, where grad mode is off
+        x = x.detach().clone().requires_grad_()
+        (g,) = torch.autograd.grad(_act(act, x).sum(), x)
+    return g
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False, dact_in=None, residual=None, alpha=1.0, out=None,
+         out_f32=False, splits=None):
+    A = a.float().t() if a_mn else a.float()
+    Bm = b.float() if b_mn else b.float().t()
+    d = alpha * (A @ Bm)
+    if bias is not None:
+        d = d + bias.float()
+    aux = None
+    if dact_in is not None:
+        aux = _act(act, dact_in.float()).to(BF)
+        d = d * _dact(act, dact_in.float())
+    else:
+        aux = d.to(BF)
+        d = _act(act, d)
+    if residual is not None:
+        d = d + residual.float()
+    d = d if out_f32 else d.to(BF)
+    return (d, aux) if aux_out else d
+
+
+def layernorm_fwd(x, w, b, eps, add0=None, add1=None, add_period=0, want_sum=False):
+    s = x.float()
+    if add0 is not None or add1 is not None:
+        rows = s.shape[0]
+        r = torch.arange(rows) % add_period
+        if add0 is not None:
+            s = s + add0.float()[r]
+        if add1 is not None:
+            s = s + (r == 0).float()[:, None] * add1.float()[None, :]
+        s = s.to(BF).float()
+    mean = s.mean(-1)
+    rstd = torch.rsqrt(s.var(-1, unbiased=False) + eps)
+    y = ((s - mean[:, None]) * rstd[:, None] * w.float() + b.float()).to(BF)
+    return y, (s.to(BF) if want_sum else None), mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, w, dw32, db32, dadd=None):
+    xh = (x.float() - mean[:, None]) * rstd[:, None]
+    gy = dy.float() * w.float()
+    dx = rstd[:, None] * (gy - gy.mean(-1, keepdim=True) - xh * (gy * xh).mean(-1, keepdim=True))
+    if dadd is not None:
+        dx = dx + dadd.float()
+    dw32 += (dy.float() * xh).sum(0)
+    db32 += dy.float().sum(0)
+    return dx.to(BF)
+
+
+def act_layernorm_fwd(u, act, w, b, eps):
+    g = _act(act, u.float())
+    mean = g.mean(-1)
+    rstd = torch.rsqrt(g.var(-1, unbiased=False) + eps)
+    return ((g - mean[:, None]) * rstd[:, None] * w.float() + b.float()).to(BF), mean, rstd
+
+
+def act_layernorm_bwd(dy, u, act, mean, rstd, w, dw32, db32):
+    g = _act(act, u.float())
+    xh = (g - mean[:, None]) * rstd[:, None]
+    gy = dy.float() * w.float()
+    dg = rstd[:, None] * (gy - gy.mean(-1, keepdim=True) - xh * (gy * xh).mean(-1, keepdim=True))
+    dw32 += (dy.float() * xh).sum(0)
+    db32 += dy.float().sum(0)
+    return (dg * _dact(act, u.float())).to(BF)
+
+
+def mask_rows(x, drop, inplace=False):
+    y = x * (1 - drop.to(x.dtype))[:, None]
+    if inplace:
+        x.copy_(y)
+        return x
+    return y
+
+
+def embed_layernorm_fwd(word, ids, pos, L, type_table, type_ids, w, b, eps):
+    rows = ids.numel()
+    s = (word.float()[ids] + pos.float()[torch.arange(rows) % L] + type_table.float()[type_ids]).to(BF)
+    y, _, mean, rstd = layernorm_fwd(s, w, b, eps)
+    return y, s, mean, rstd
+
+
+def _attn(qkv, B, L, H, hd, key_bias):
+    W = H * hd
+    q, k, v = (qkv[:, i * W:(i + 1) * W].reshape(B, L, H, hd).transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    if key_bias is not None:
+        s = s + key_bias[:, None, None, :]
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, W), torch.logsumexp(s, -1)
+
+
+def attention_fwd(qkv, B, L, H, hd, key_bias=None, **kw):
+    o, lse = _attn(qkv.float(), B, L, H, hd, key_bias)
+    return o.to(BF), lse
+
+
+def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, **kw):
+    with torch.enable_grad():
+        x = qkv.float().detach().requires_grad_()
+        out, _ = _attn(x, B, L, H, hd, key_bias)
+        (g,) = torch.autograd.grad(out, x, d_o.float())
+    return g.to(BF)
+
+
+def act_fwd(x, act):
+    return _act(act, x.float()).to(BF)
+
+
+def rowsum_periodic(x, out32, period=1):
+    rows, W = x.shape
+    out32.view(period, W).add_(x.float().view(rows // period, period, W).sum(0))
+
+
+def scatter_add_rows(x, ids, out32, skip_id=-1):
+    keep = ids != skip_id
+    out32.index_add_(0, ids[keep], x.float()[keep])
+
+
+def cast_f32_bf16(x32, scale=1.0):
+    return (x32 * scale).to(BF)
+
+
+def rownorm_fwd(x, eps=1e-12):
+    inv = 1.0 / x.float().norm(dim=-1).clamp_min(eps)
+    return (x.float() * inv[:, None]).to(BF), inv
+
+
+def rownorm_bwd(dy32, x, inv):
+    y = x.float() * inv[:, None]
+    return ((dy32 - y * (dy32 * y).sum(-1, keepdim=True)) * inv[:, None]).to(BF)
+
+
+def im2row(img, p, Kp):
+    B, C, H, W = img.shape
+    g = H // p
+    x = img.reshape(B, C, g, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, g * (W // p), C * p * p)
+    out = torch.zeros(B, g * (W // p) + 1, Kp, dtype=BF)
+    out[:, 1:, : C * p * p] = x
+    return out.reshape(-1, Kp)
+
+
+@contextlib.contextmanager
+def patched():
+    """Swaps the kernel wrappers of b200mm.ops for the stand-ins above (restored on exit)."""
+    from b200mm import ops
+
+    names = [n for n, f in globals().items() if callable(f) and not n.startswith("_") and hasattr(ops, n) and n not in ("patched",)]
+    saved = {n: getattr(ops, n) for n in names}
+    try:
+        for n in names:
+            setattr(ops, n, globals()[n])
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

@@ -91,3 +91,29 @@ def test_golden_state_dict_loads_strict(golden_dir):
     m = CNCLIP(**fx["config"])
     missing, unexpected = m.load_state_dict(fx["state_dict"], strict=True)
     assert not missing and not unexpected
+
+
+def test_m2_encoder_state_dict_keys_match_reference(golden_dir):
+    """M2Encoder carries the reference's parameter names and shapes (prj/M2_Encoder: BEiT3 + backbone_vl Encoder + ITC heads),
+    checked against the state dict of the unmodified reference classes stored in tests/golden/m2_tiny.pt."""
+    from b200mm.modules import M2Encoder
+
+    fx = torch.load(os.path.join(golden_dir, "m2_tiny.pt"), weights_only=False)
+    c = fx["config"]
+    m = M2Encoder(image_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"],
+                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"])
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in fx["state_dict"].items()}
+    assert set(ref) <= set(ours), sorted(set(ref) - set(ours))[:5]
+    extra = set(ours) - set(ref)
+    assert all(k.startswith(("norm.", "pooler.")) for k in extra), sorted(extra)[:5]  # VLMo's own unused members (vlmo_module.py:176-179)
+    for k in ref:
+        assert ours[k] == ref[k], (k, ours[k], ref[k])
+    m.load_state_dict(fx["state_dict"], strict=False)
+    if ref_loader.available():  # and against the live reference classes
+        m2 = ref_loader.load_m2()
+        args = m2.EncoderConfig(img_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], multiway=True, no_output_layer=True,
+                                encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"], encoder_layers=c["layers"],
+                                encoder_ffn_embed_dim=4 * c["W"], max_text_len=c["L"])
+        live = {"backbone." + k: tuple(v.shape) for k, v in m2.BEiT3(args).state_dict().items()}
+        assert all(ours[k] == s for k, s in live.items())
