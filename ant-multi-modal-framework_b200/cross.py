@@ -1,0 +1,211 @@
+"""Stage-2 (cross-modal) retrieval scoring of prj/base_vtp on the b200mm kernels.
+
+Reference (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py):
+  _cross_similarity             :33-89    every text against every video, walked in blocks of 5 texts; each block builds its
+                                          [5·B_v, S_t + S_v, H] input by unsqueeze/repeat/view + torch.cat inside get_cross_output
+  _cross_similarity_hard_mining :91-144   per local text a Python iteration: topk over its level-1 row, gather the chosen videos,
+                                          one cross-encoder call at batch bsz
+  forward_stage2                :389-443  'median' row weights + get_mil_nce_loss on the [bsz, bsz] score matrix
+  similarity_dense              :24-28    Linear(E, 2E) → ReLU → Linear(2E, 1) on the pooled CLS (dropout p = 0 here)
+
+B200 form: a pair list (text index, video index) is scored in large blocks — one gather kernel writes the concatenated token rows
+of a whole block straight from the two token tables (no repeat/cat intermediates; its backward is one scatter-add per table), the
+BERT layers run once per block on the tcgen05 kernels at GEMM-friendly row counts instead of once per 5 texts / per mined row, and
+the hard-negative SELECTION stays index-exact with the reference (same torch.topk calls, row by row — it is O(bsz) tiny launches of
+index work; the O(bsz²) encoder work is what is batched). Block size is bounded by `max_pairs` (activation memory ≈ 50 KB per pair
+and layer at S = 86, H = 768; default 8192 pairs ≈ 5 GB per saved layer set).
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import functional as Fn
+from . import ops
+from .distributed import gather_tensor
+
+BF16 = torch.bfloat16
+
+
+def _bf16(t):
+    return t if t.dtype == BF16 else t.to(BF16)
+
+
+class GatherRowsFn(Function):
+    """out[r] = table[ids[r]]; backward sums the row gradients back per table row (fp32 atomics, one bf16 rounding)."""
+
+    @staticmethod
+    def forward(ctx, table, ids):
+        ctx.save_for_backward(ids)
+        ctx.n = table.shape[0]
+        return ops.gather_rows(table.contiguous(), ids)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        acc = torch.zeros((ctx.n, dy.shape[1]), device=dy.device, dtype=torch.float32)
+        ops.scatter_add_rows(dy.contiguous(), ids, acc)
+        return ops.cast_f32_bf16(acc), None
+
+
+class SimilarityHeadFn(Function):
+    """nn.Sequential(Linear(E, 2E), ReLU, Linear(2E, 1)) on [P, E] → f32 [P]  (univl_video_ret.py:24-28)."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2):
+        h_pre = ops.gemm(x, w0, bias=b0)
+        h = ops.relu_fwd(h_pre)
+        w2p = torch.zeros((8, w2.shape[1]), device=x.device, dtype=BF16)  # N = 1 padded to the 8-column granularity of the GEMM
+        w2p[0] = w2[0]
+        b2p = torch.zeros(8, device=x.device, dtype=BF16)
+        b2p[0] = b2[0]
+        out = ops.gemm(h, w2p, bias=b2p, out_f32=True)
+        ctx.save_for_backward(x, w0, h_pre, w2p)
+        return out[:, 0].contiguous()
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w0, h_pre, w2p = ctx.saved_tensors
+        P = x.shape[0]
+        dop = torch.zeros((P, 8), device=x.device, dtype=BF16)
+        dop[:, 0] = dout
+        h = ops.relu_fwd(h_pre)
+        d_w2 = ops.gemm(dop, h, a_mn=True, b_mn=True)[:1]
+        vg = Fn._VecGrads(x.device, [8, w0.shape[0]])
+        ops.rowsum_periodic(dop, vg[0])
+        d_h = ops.gemm(dop, w2p, b_mn=True)
+        d_pre = ops.relu_bwd(d_h, h_pre)
+        d_w0 = ops.gemm(d_pre, x, a_mn=True, b_mn=True)
+        ops.rowsum_periodic(d_pre, vg[1])
+        dx = ops.gemm(d_pre, w0, b_mn=True)
+        d_b2, d_b0 = vg.finish()
+        return dx, d_w0, d_b0, d_w2.contiguous(), d_b2[:1].contiguous()
+
+
+class MilNceMatrixFn(Function):
+    """get_mil_nce_loss (univl_video_ret.py:146-197, n_pair = 1) on an explicit f32 score matrix with optional row weights."""
+
+    @staticmethod
+    def forward(ctx, S, weight):
+        S = S.float().contiguous()
+        lse, loss_sum = ops.mil_nce_matrix_fwd(S, weight)
+        ctx.save_for_backward(S, lse, weight)
+        return loss_sum / S.shape[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        S, lse, weight = ctx.saved_tensors
+        return ops.mil_nce_matrix_bwd(S, weight, lse, g.float().contiguous()), None
+
+
+def mil_nce_matrix_loss(sim_matrix, weight_vector=None):
+    w = None if weight_vector is None else weight_vector.detach().float().contiguous()
+    return MilNceMatrixFn.apply(sim_matrix, w)
+
+
+def hard_mining_indices(l1_simi, beg_idx, bsz, method="top_k"):
+    """The reference's negative selection, row by row with the same torch.topk calls (univl_video_ret.py:107-131): returns int64
+    [bsz, bsz] global video indices, slot i of row i = the positive beg_idx + i. `l1_simi` is left untouched."""
+    out = torch.empty((bsz, bsz), dtype=torch.long, device=l1_simi.device)
+    for i in range(bsz):
+        raw = beg_idx + i
+        row = l1_simi[raw].clone()
+        if method == "top_k":
+            row[raw] -= 100.0
+            _, chosen = torch.topk(row, bsz, sorted=False)
+        elif method == "nearliest":
+            row = (row - row[raw]).abs()
+            row[raw] = 100.0
+            _, chosen = torch.topk(row, bsz, sorted=False, largest=False)
+        else:
+            raise ValueError(f"re_sample_method {method!r}: expected 'top_k' or 'nearliest'")
+        out[i] = chosen
+        out[i, i] = raw
+    return out
+
+
+def hard_mining_weights(l1_diag, method="top_k"):
+    """'median' row weights of forward_stage2 (univl_video_ret.py:414-430), vectorised; bit-identical to the reference loop,
+    including its read of the diagonal AFTER the in-place −100 of the 'top_k' selection (:113)."""
+    d = l1_diag.detach().float()
+    if method == "top_k":
+        d = d - 100.0
+    mean, mn = d.mean(), d.min()
+    return torch.where(d > mean, torch.clamp_min((mean - mn) / (d - mn), 0.2), torch.ones_like(d))
+
+
+class CrossScorer(nn.Module):
+    """Scores (text, video) pairs with the cross encoder of `text_encoder` (a B200RobertBertEncoder: `.encoder` = BertEncoder whose
+    layers are shared with the text tower, `.text_projection`; univl_video_base.py:47-54, arch 'clip') and owns `similarity_dense`
+    under the reference's parameter names (similarity_dense.0.*, similarity_dense.2.*)."""
+
+    def __init__(self, text_encoder, out_dim, max_pairs=8192):
+        super().__init__()
+        self.text_encoder = text_encoder
+        self.similarity_dense = nn.Sequential(nn.Linear(out_dim, out_dim * 2), nn.ReLU(True), nn.Linear(out_dim * 2, 1))
+        self.max_pairs = max_pairs
+
+    # ---- one block of aligned pairs -------------------------------------------------------------------------------------
+    def _score_pairs(self, text2d, St, text_mask, vis2d, Sv, vis_mask, ti, vi):
+        """text2d [Bt·St, H], vis2d [Bv·Sv, H] token tables; ti / vi int64 [P] pair lists → f32 [P] logits."""
+        P, S = ti.numel(), St + Sv
+        dev = text2d.device
+        n_text = text2d.shape[0]
+        # row r = (p, s) of the concatenated input reads text row ti[p]·St + s or visual row vi[p]·Sv + (s − St) of the stacked table
+        s_idx = torch.arange(S, device=dev)
+        ids = torch.where(s_idx[None, :] < St, ti[:, None] * St + s_idx[None, :], n_text + vi[:, None] * Sv + (s_idx[None, :] - St))
+        table = torch.cat([text2d, vis2d], dim=0)
+        embed = GatherRowsFn.apply(table, ids.reshape(-1).contiguous())
+        mask = torch.cat([text_mask[ti], vis_mask[vi]], dim=1)  # [P, S] (small integer gather)
+        key_bias = ((1.0 - mask.float()) * -10000.0).contiguous()  # univl_video_base.py:244-245
+        enc = self.text_encoder.encoder
+        x = embed
+        for layer in enc.layer:
+            x = layer.forward_tokens(x, key_bias, P, S)
+        proj = self.text_encoder.text_projection
+        if proj is not None:
+            pooled = Fn.ClsHeadFn.apply(x, None, None, _bf16(proj), P, S, 0.0)
+        else:
+            pooled = x.view(P, S, -1)[:, 0, :].contiguous()
+        d = self.similarity_dense
+        return SimilarityHeadFn.apply(pooled, _bf16(d[0].weight), _bf16(d[0].bias), _bf16(d[2].weight), _bf16(d[2].bias))
+
+    def score_pair_list(self, sequence_output, attention_mask, visual_output, video_mask, ti, vi):
+        Bt, St, H = sequence_output.shape
+        Bv, Sv, _ = visual_output.shape
+        text2d = _bf16(sequence_output).reshape(Bt * St, H)
+        vis2d = _bf16(visual_output).reshape(Bv * Sv, H)
+        outs = []
+        for lo in range(0, ti.numel(), self.max_pairs):
+            sl = slice(lo, lo + self.max_pairs)
+            outs.append(self._score_pairs(text2d, St, attention_mask, vis2d, Sv, video_mask, ti[sl].contiguous(), vi[sl].contiguous()))
+        return torch.cat(outs) if len(outs) > 1 else outs[0]
+
+    # ---- reference entry points ------------------------------------------------------------------------------------------
+    def cross_similarity(self, sequence_output, visual_output, attention_mask, video_mask, num_clips=1):
+        """_cross_similarity (:33-89): [B_text, B_video·num_clips] f32 logits (visual_output is already [B_video·num_clips, S_v, H])."""
+        Bt, Bv = sequence_output.shape[0], visual_output.shape[0]
+        dev = sequence_output.device
+        ti = torch.arange(Bt, device=dev).repeat_interleave(Bv)
+        vi = torch.arange(Bv, device=dev).repeat(Bt)
+        return self.score_pair_list(sequence_output, attention_mask, visual_output, video_mask, ti, vi).view(Bt, Bv)
+
+    def cross_similarity_hard_mining(self, vis_input, cap_input, l1_simi_matrix, re_sample_method="top_k", group=None):
+        """_cross_similarity_hard_mining (:91-144): same tuple arguments as the reference; returns f32 [bsz, bsz] logits whose column i
+        of row i is the positive. Gathered visual tokens carry gradient home through gather_tensor's backward."""
+        (sequence_output, attention_mask, _text_l1, bsz, _cap) = cap_input
+        (visual_output, video_mask, _video_l1, _num_clips, _img) = vis_input
+        visual_all = gather_tensor(visual_output, method="cat", back_gradient=True, pad_tensors=True)
+        mask_all = gather_tensor(video_mask, method="cat", back_gradient=False, pad_tensors=True)
+        rank = torch.distributed.get_rank(group) if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        beg_idx = rank * bsz  # equal per-rank batches (the reference all-gathers bsz; DistributedSampler gives equal sizes)
+        chosen = hard_mining_indices(l1_simi_matrix.detach(), beg_idx, bsz, re_sample_method)
+        ti = torch.arange(bsz, device=sequence_output.device).repeat_interleave(bsz)
+        return self.score_pair_list(sequence_output, attention_mask, visual_all, mask_all, ti, chosen.reshape(-1)).view(bsz, bsz)
+
+    def level2_loss(self, l2_simi, l1_simi_matrix=None, beg_idx=0, re_weight_method=None, re_sample_method="top_k"):
+        """forward_stage2 (:403-433): MIL-NCE on the [bsz, bsz] stage-2 scores, optionally with the 'median' row weights."""
+        w = None
+        if re_weight_method == "median":
+            B = l2_simi.shape[0]
+            w = hard_mining_weights(torch.diagonal(l1_simi_matrix[beg_idx: beg_idx + B, beg_idx: beg_idx + B]), re_sample_method)
+        return mil_nce_matrix_loss(l2_simi, w)

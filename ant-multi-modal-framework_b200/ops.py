@@ -447,3 +447,65 @@ def ema_update(pk32, pq, m):
         raise _lib.B200mmError("b200mm.ema_update: tensors must be contiguous")
     _lib.check(lib.b200mm_ema_update(_ptr(pk32), _ptr(pq), int(pq.dtype == BF16), pk32.numel(), m, _stream()), "b200mm_ema_update")
     _count(1)
+
+
+def gather_rows(src, ids):
+    """out[r, :] = src[ids[r], :] (bf16 [n, W], int64 [rows]) — bit-exact row gather."""
+    lib = _lib.load()
+    _req(src, "src", BF16, 2)
+    _req(ids, "ids", torch.int64, 1)
+    if not (src.is_contiguous() and ids.is_contiguous()):
+        raise _lib.B200mmError("b200mm.gather_rows: src and ids must be contiguous")
+    out = torch.empty((ids.numel(), src.shape[1]), device=src.device, dtype=BF16)
+    _lib.check(lib.b200mm_gather_rows(_ptr(src), _ptr(ids), _ptr(out), ids.numel(), src.shape[0], src.shape[1], _stream()), "b200mm_gather_rows")
+    _count(1)
+    return out
+
+
+def relu_fwd(x):
+    lib = _lib.load()
+    _req(x, "x", BF16)
+    if not x.is_contiguous():
+        raise _lib.B200mmError("b200mm.relu_fwd: x must be contiguous")
+    y = torch.empty_like(x)
+    _lib.check(lib.b200mm_relu_fwd(_ptr(x), _ptr(y), x.numel(), _stream()), "b200mm_relu_fwd")
+    _count(1)
+    return y
+
+
+def relu_bwd(dy, x):
+    lib = _lib.load()
+    _req(dy, "dy", BF16)
+    _req(x, "x", BF16)
+    if not (x.is_contiguous() and dy.is_contiguous()):
+        raise _lib.B200mmError("b200mm.relu_bwd: tensors must be contiguous")
+    dx = torch.empty_like(x)
+    _lib.check(lib.b200mm_relu_bwd(_ptr(dy), _ptr(x), _ptr(dx), x.numel(), _stream()), "b200mm_relu_bwd")
+    _count(1)
+    return dx
+
+
+def mil_nce_matrix_fwd(S, w=None):
+    """S f32 [B, B] (row stride free), w f32 [B] or None -> (lse [B], loss_sum scalar tensor = sum_j w_j (lse_j - S_jj))."""
+    lib = _lib.load()
+    _req(S, "S", torch.float32, 2)
+    if S.shape[0] != S.shape[1] or S.stride(1) != 1:
+        raise _lib.B200mmError(f"b200mm.mil_nce_matrix_fwd: S must be square with unit inner stride, got {tuple(S.shape)} / {S.stride()}")
+    if w is not None:
+        _req(w, "w", torch.float32, 1)
+    B = S.shape[0]
+    lse = torch.empty(B, device=S.device, dtype=torch.float32)
+    loss_sum = torch.zeros((), device=S.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_mil_nce_matrix_fwd(_ptr(S), S.stride(0), _ptr(w), _ptr(lse), _ptr(loss_sum), B, _stream()), "b200mm_mil_nce_matrix_fwd")
+    _count(1)
+    return lse, loss_sum
+
+
+def mil_nce_matrix_bwd(S, w, lse, gout):
+    lib = _lib.load()
+    B = S.shape[0]
+    dS = torch.empty((B, B), device=S.device, dtype=torch.float32)
+    _lib.check(lib.b200mm_mil_nce_matrix_bwd(_ptr(S), S.stride(0), _ptr(w), _ptr(lse), _ptr(_req(gout, "gout", torch.float32)), _ptr(dS), B, _stream()),
+               "b200mm_mil_nce_matrix_bwd")
+    _count(1)
+    return dS

@@ -31,6 +31,9 @@ FLOP_PER_PAIR = {  # algorithmic fwd+bwd FLOPs per pair, SURVEY.md §8d (GEMMs 2
     "ViT-L-14": 526.0e9,
     "ViT-B-16": 145.0e9,
     "ViT-H-14": None,
+    # M2-Encoder (BEiT-3 multiway, 197 image tokens + 52 text tokens through the same 21+3 / 9+3 layers), same counting rule
+    "M2-Encoder-1B": 3 * (24 * 1024**2 + 4 * 197 * 1024) * 24 * 197 + 3 * (24 * 1024**2 + 4 * 52 * 1024) * 24 * 52,
+    "M2-Encoder-0.4B": 3 * (24 * 768**2 + 4 * 197 * 768) * 12 * 197 + 3 * (24 * 768**2 + 4 * 52 * 768) * 12 * 52,
 }
 
 
@@ -103,8 +106,30 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class _M2Step(torch.nn.Module):
+    """M2-Encoder ITC step behind the (image, text) -> loss interface of the bench: text_masks = ids != [PAD]."""
+
+    def __init__(self, m2):
+        super().__init__()
+        self.m2 = m2
+
+    def parameters(self, recurse=True):
+        return self.m2.parameters(recurse)
+
+    def contrastive_loss(self, image, text, group=None):
+        return self.m2.itc_loss(image, text, (text != 0).long(), group)
+
+
 def build_model(name, device, ckpt_every, keep_act=0):
-    from b200mm.modules import CNCLIP, CONFIGS
+    from b200mm.modules import CNCLIP, CONFIGS, M2_CONFIGS, M2Encoder
+
+    if name in M2_CONFIGS:
+        cfg = dict(M2_CONFIGS[name])
+        torch.manual_seed(0)
+        m2 = M2Encoder(**cfg).to(device).to(torch.bfloat16).train()
+        if ckpt_every > 0:
+            m2.set_grad_checkpointing(True)
+        return _M2Step(m2), dict(image_resolution=cfg["image_size"], vocab_size=cfg["vocab_size"], vision_layers=cfg["encoder_layers"])
 
     cfg = dict(CONFIGS[name])
     cfg["text_hidden_dropout_prob"] = 0.0  # the fused kernels implement p = 0; stated in `config.dropout`
@@ -253,7 +278,9 @@ def run_ours(args):
             "metric": METRIC, "value": round(pairs_per_s, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (seeded N(0,1) images, random ids with [CLS]/[SEP]/[PAD]; random-init weights, reference init)",
-            "config": {"workload": f"BASELINE.json configs[{1 if world == 1 else 2}]: CNCLIP {args.model} + BERT-base, fwd + fused contrastive loss + bwd",
+            "config": {"workload": (f"BASELINE.json configs[{1 if world == 1 else 2}]: CNCLIP {args.model} + BERT-base, fwd + fused contrastive loss + bwd"
+                                    if args.model in FLOP_PER_PAIR and not args.model.startswith("M2") else
+                                    f"prj/M2_Encoder {args.model} (BEiT-3 multiway): infer_image + infer_text + symmetric ITC on both head pairs, fwd + bwd"),
                        "model": args.model, "per_gpu_batch": B, "global_batch": B * world, "image_res": res, "seq_len": L,
                        "parallelism": f"dp{world}" + (" + embedding all-gather / grad reduce-scatter, DDP grad all-reduce in the timed region" if world > 1 else ""),
                        "dropout": 0.0, "recompute": f"GradCache two-pass, micro-batch {args.micro_batch} (second forward not counted)" if args.micro_batch else f"checkpoint every {args.ckpt_every} ViT block(s)" if args.ckpt_every else f"none (LN outputs recomputed; activated MLP hidden recomputed in {max(0, cfg['vision_layers'] - args.keep_act)} of {cfg['vision_layers']} ViT blocks)",

@@ -169,6 +169,19 @@ int b200mm_act_layernorm_bwd(const void* dy, const void* u, int32_t act, const f
 /* y[r,:] = drop[r] ? 0 : x[r,:]  (bf16 [rows, W], drop = bytes): Encoder.forward zeroes the padded token rows,
  * prj/M2_Encoder/vlmo/torchscale/architecture/encoder.py:440; the same call masks the gradient in backward. y may alias x. */
 int b200mm_mask_rows(const void* x, const uint8_t* drop, void* y, int64_t rows, int32_t W, void* stream);
+/* Stage-2 (cross-modal) retrieval helpers, prj/base_vtp/roi_univl/univl/model/univl_video_ret.py.
+ * gather_rows: out[r,:] = src[ids[r],:] (bf16 [n_src, W] -> [rows, W], bit-exact; ids outside [0, n_src) give a zero row). One pass builds
+ * the [text ; visual] token rows of many (text, video) pairs, replacing the unsqueeze/repeat/view/cat copies of _cross_similarity (:52-78)
+ * and _cross_similarity_hard_mining (:101-131); its backward is b200mm_scatter_add_rows. */
+int b200mm_gather_rows(const void* src, const int64_t* ids, void* out, int64_t rows, int64_t n_src, int32_t W, void* stream);
+/* ReLU of the similarity head nn.Sequential(Linear, ReLU, Linear) (:24-28): y = max(x, 0); dx = dy * [x > 0]; bf16, n % 8 == 0. */
+int b200mm_relu_fwd(const void* x, void* y, int64_t n, void* stream);
+int b200mm_relu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
+/* get_mil_nce_loss (:146-197) on an explicit square f32 score matrix S [B, ld] (n_pair 1) with optional row weights w [B] (forward_stage2
+ * :414-433): lse[j] = log(sum_i e^{S[i,j]} + sum_{k!=j} e^{S[j,k]}), *loss_sum += sum_j w_j (lse[j] - S[j,j]) (caller zero-fills and divides by B).
+ * bwd: dS [B,B] f32 = (*gout / B) * dLoss/dS with the saved lse. */
+int b200mm_mil_nce_matrix_fwd(const float* S, int64_t ld, const float* w, float* lse, float* loss_sum, int32_t B, void* stream);
+int b200mm_mil_nce_matrix_bwd(const float* S, int64_t ld, const float* w, const float* lse, const float* gout, float* dS, int32_t B, void* stream);
 /* y = act(x), bf16, n % 8 == 0 (activation recompute in backward: QuickGELU clip/model.py:222-224, erf-GELU modeling_bert.py:31-37) */
 int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream);
 /* out[(row % period), :] += in[row, :]  (f32 atomics, caller zero-fills): period 1 = bias gradient of nn.Linear,

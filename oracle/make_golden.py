@@ -224,8 +224,73 @@ def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, pat
     print(name, "loss", float(loss.detach()), "params", sum(p.numel() for p in model.parameters()), "with grad", len(fx["grads"]))
 
 
+def make_stage2():
+    """Stage-2 cross-modal scoring with the UNMODIFIED reference functions (ref_loader.load_stage2 / build_stage2_self):
+    `_cross_similarity` on a ragged (7 texts x 4 videos, block size 5 + 2) problem and `_cross_similarity_hard_mining` for both
+    re-sampling methods, each followed by get_mil_nce_loss with the 'median' row weights of forward_stage2 (:414-433)."""
+    out = {}
+    me = ref_loader.build_stage2_self(hidden=64, heads=2, layers=2, inter=128, out_dim=32, seed=0)
+    sd = {"cross_encoder." + k: v.detach().clone() for k, v in me.module.cross_encoder.state_dict().items()}
+    sd["text_projection"] = me.module.text_encoder.text_projection.detach().clone()
+    sd.update({"similarity_dense." + k: v.detach().clone() for k, v in me.similarity_dense.state_dict().items()})
+    out["state_dict"] = sd
+    out["config"] = dict(hidden=64, heads=2, layers=2, inter=128, out_dim=32)
+    params = dict(me.named_parameters())
+
+    def names(n):  # reference parameter name -> fixture state-dict name
+        return n.replace("module.cross_encoder.", "cross_encoder.").replace("module.text_encoder.text_projection", "text_projection")
+
+    torch.manual_seed(11)
+    Bt, St, Bv, Sv, H = 7, 6, 4, 3, 64
+    seq = torch.randn(Bt, St, H, requires_grad=True)
+    vis = torch.randn(Bv, Sv, H, requires_grad=True)
+    am = torch.ones(Bt, St, dtype=torch.long)
+    am[2, 4:] = 0
+    am[5, 3:] = 0
+    vm = torch.ones(Bv, Sv, dtype=torch.long)
+    vm[1, 2:] = 0
+    logits = me._cross_similarity(seq, vis, am, vm, 1)
+    logits.square().sum().backward()
+    out["cross"] = dict(seq=seq.detach(), vis=vis.detach(), am=am, vm=vm, logits=logits.detach(), d_seq=seq.grad.clone(), d_vis=vis.grad.clone(),
+                        grads={names(n): p.grad.clone() for n, p in params.items() if p.grad is not None})
+    for method in ["top_k", "nearliest"]:
+        for p in params.values():
+            p.grad = None
+        me.config.re_sample_method = method
+        torch.manual_seed(12)
+        B = 6
+        seq = torch.randn(B, St, H, requires_grad=True)
+        vis = torch.randn(B, Sv, H, requires_grad=True)
+        am = torch.ones(B, St, dtype=torch.long)
+        am[1, 4:] = 0
+        vm = torch.ones(B, Sv, dtype=torch.long)
+        vm[3, 1:] = 0
+        l1 = torch.randn(B, B) + 2.0 * torch.eye(B)
+        l1c = l1.clone()
+        l2 = me._cross_similarity_hard_mining((vis, vm, None, 1, None), (seq, am, None, B, None), l1c)
+        # forward_stage2 :414-433 verbatim (single process: beg_idx = 0)
+        l1_diag = torch.diag(l1c[0:B, 0:B])
+        l1_median, l1_minimum = torch.mean(l1_diag), torch.min(l1_diag)
+        weight_vector = torch.ones(l1_diag.shape, dtype=l1_diag.dtype)
+        for i in range(len(l1_diag)):
+            if l1_diag[i] > l1_median:
+                weight_vector[i] = max((l1_median - l1_minimum) / (l1_diag[i] - l1_minimum), 0.2)
+        mil = l2.unsqueeze(1).repeat([1, 1, 1, 1]).view(B, B)
+        loss = me.get_mil_nce_loss(mil, B, weight_vector=weight_vector)
+        loss_unweighted = me.get_mil_nce_loss(mil, B).detach()
+        loss.backward()
+        out["hard_" + method] = dict(seq=seq.detach(), vis=vis.detach(), am=am, vm=vm, l1=l1, logits=l2.detach(), weights=weight_vector,
+                                     loss=loss.detach(), loss_unweighted=loss_unweighted, d_seq=seq.grad.clone(), d_vis=vis.grad.clone(),
+                                     grads={names(n): p.grad.clone() for n, p in params.items() if p.grad is not None})
+    torch.save(out, os.path.join(OUT, "stage2.pt"))
+    print("stage2.pt", tuple(out["cross"]["logits"].shape), {k: float(v["loss"]) for k, v in out.items() if k.startswith("hard")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--stage2-only" in sys.argv:
+        make_stage2()
+        sys.exit(0)
     if "--m2-only" in sys.argv:
         make_m2()
         sys.exit(0)
@@ -243,3 +308,4 @@ if __name__ == "__main__":
     make_losses()
     make_retrieval()
     make_m2()
+    make_stage2()

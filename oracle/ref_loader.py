@@ -192,3 +192,58 @@ def load_m2():
     ns.multiway = importlib.import_module("vlmo.torchscale.component.multiway_network")
     _loaded["m2"] = ns
     return ns
+
+
+def load_stage2():
+    """Unmodified stage-2 (cross-modal) retrieval arithmetic of prj/base_vtp, AST-extracted because the modules import the whole
+    antmmf package: `_cross_similarity` (univl_video_ret.py:33-89), `_cross_similarity_hard_mining` (:91-144), `get_mil_nce_loss`
+    (:146-197), `get_cross_output` / `_align_text_to_video_clips` (univl_video_base.py:229-307), `split_encoder_output`
+    (univl_base.py:17-36). `gather_tensor` / `all_gather` / `get_rank` come from the real antmmf/utils/distributed_utils.py
+    (single process: identity / [x] / 0). Returns a namespace of plain functions taking `self` first."""
+    if "stage2" in _loaded:
+        return _loaded["stage2"]
+    ns0 = load()
+    du = ns0.distributed_utils
+    split = _extract_functions("prj/base_vtp/roi_univl/univl/model/univl_base.py", ["split_encoder_output"])
+    base = _extract_functions("prj/base_vtp/roi_univl/univl/model/univl_video_base.py", ["get_cross_output", "_align_text_to_video_clips"],
+                              extra_ns=split)
+    ret = _extract_functions("prj/base_vtp/roi_univl/univl/model/univl_video_ret.py",
+                             ["_cross_similarity", "_cross_similarity_hard_mining", "get_mil_nce_loss"],
+                             extra_ns=dict(gather_tensor=du.gather_tensor, all_gather=du.all_gather, get_rank=du.get_rank))
+    ns = types.SimpleNamespace(**split, **base, **ret)
+    _loaded["stage2"] = ns
+    return ns
+
+
+def build_stage2_self(hidden=64, heads=2, layers=2, inter=128, out_dim=32, seed=0, re_sample_method="top_k"):
+    """A stand-in for `UnivlForVideoTextRetrieval` holding exactly the members the extracted stage-2 functions touch:
+    .module.{cross_encoder = reference BertEncoder, arch_type 'clip', text_encoder.text_projection, get_cross_output, …},
+    .similarity_dense (univl_video_ret.py:24-28), .dropout (p set to 0 for parity), .config.re_sample_method."""
+    import torch
+    from torch import nn
+
+    ns = load()
+    s2 = load_stage2()
+    torch.manual_seed(seed)
+    cfg = ns.configuration_bert.BertConfig(vocab_size_or_config_json_file=64, hidden_size=hidden, num_hidden_layers=layers,
+                                           num_attention_heads=heads, intermediate_size=inter, hidden_act="gelu", hidden_dropout_prob=0.0,
+                                           attention_probs_dropout_prob=0.0, max_position_embeddings=64)
+    module = nn.Module()
+    module.cross_encoder = ns.modeling_bert.BertEncoder(cfg)
+    for m in module.cross_encoder.modules():
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(0.0, 0.05)
+            m.bias.data.normal_(0.0, 0.05)
+    module.arch_type = "clip"
+    module.text_encoder = nn.Module()
+    module.text_encoder.text_projection = nn.Parameter(torch.randn(hidden, out_dim) * hidden ** -0.5)
+    module.get_cross_output = types.MethodType(s2.get_cross_output, module)
+    module._align_text_to_video_clips = types.MethodType(s2._align_text_to_video_clips, module)
+    me = nn.Module()
+    me.module = module
+    me.dropout = nn.Dropout(0.0)
+    me.similarity_dense = nn.Sequential(nn.Linear(out_dim, out_dim * 2), nn.ReLU(True), nn.Linear(out_dim * 2, 1))
+    me.config = types.SimpleNamespace(re_sample_method=re_sample_method, hidden_size=out_dim)
+    for name in ["_cross_similarity", "_cross_similarity_hard_mining", "get_mil_nce_loss"]:
+        setattr(me, name, types.MethodType(getattr(s2, name), me))
+    return me

@@ -345,3 +345,88 @@ def m2_itc_loss(sd, img_f, txt_f, img_fv, txt_fv):
     l1 = symmetric_info_nce(sd["logit_scale"].exp() * img_f @ txt_f.t())
     l2 = symmetric_info_nce(sd["logit_vl_scale"].exp() * img_fv @ txt_fv.t())
     return l1 + l2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Stage-2 cross-modal retrieval: blockwise N x M cross-encoder scoring and hard-negative mining
+# prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:33-144, :389-443  
+# State-dict names: "cross_encoder.layer.{i}.…" (BertEncoder), "text_projection" [H, E],
+# "similarity_dense.0.{weight,bias}" [2E, E], "similarity_dense.2.{weight,bias}" [1, 2E].
+# ----------------------------------------------------------------------------------------------------------------
+def cross_pair_logits(sd, text_seq, text_mask, vis_seq, vis_mask, heads):
+    """One cross-encoder score per ALIGNED pair p: get_cross_output (univl_video_base.py:229-271, arch 'clip', n_clips 1) —
+    concat [text ; visual] tokens and masks, additive key mask (1−m)·−10000, the BERT layers, CLS @ text_projection — followed by
+    similarity_dense = Linear → ReLU → Linear(·, 1) (univl_video_ret.py:24-28, dropout p = 0). Returns [P]."""
+    embed = torch.cat([text_seq, vis_seq], dim=1)
+    mask = torch.cat([text_mask, vis_mask], dim=1)
+    seq = bert_encoder(sd, "cross_encoder.", embed, heads, mask.to(embed.dtype))
+    pooled = seq[:, 0, :] @ sd["text_projection"]
+    h = torch.relu(pooled @ sd["similarity_dense.0.weight"].t() + sd["similarity_dense.0.bias"])
+    return (h @ sd["similarity_dense.2.weight"].t() + sd["similarity_dense.2.bias"]).squeeze(-1)
+
+
+def cross_similarity(sd, text_seq, text_mask, vis_seq, vis_mask, heads):
+    """_cross_similarity (univl_video_ret.py:33-89): every text against every video; the reference walks the texts in blocks of 5
+    (memory only) — the result is the [B_text, B_video] matrix of pair scores."""
+    Bt, Bv = text_seq.shape[0], vis_seq.shape[0]
+    ti = torch.arange(Bt).repeat_interleave(Bv)
+    vi = torch.arange(Bv).repeat(Bt)
+    return cross_pair_logits(sd, text_seq[ti], text_mask[ti], vis_seq[vi], vis_mask[vi], heads).view(Bt, Bv)
+
+
+def hard_mining_indices(l1_simi, beg_idx, bsz, method="top_k"):
+    """Negative selection of _cross_similarity_hard_mining (univl_video_ret.py:107-134), row by row with the same torch.topk
+    calls (sorted=False: the slot order is whatever topk returns on this device, exactly as in the reference). Row i of the
+    result lists the bsz global video indices scored against local text i; slot i is overwritten with the positive beg_idx + i.
+    `l1_simi` is not modified (the reference subtracts 100 from the diagonal of its detached clone in place)."""
+    out = torch.empty((bsz, bsz), dtype=torch.long, device=l1_simi.device)
+    for i in range(bsz):
+        raw = beg_idx + i
+        row = l1_simi[raw].clone()
+        if method == "top_k":
+            row[raw] -= 100.0
+            _, chosen = torch.topk(row, bsz, sorted=False)
+        elif method == "nearliest":
+            row = (row - row[raw]).abs()
+            row[raw] = 100.0
+            _, chosen = torch.topk(row, bsz, sorted=False, largest=False)
+        else:
+            raise ValueError(method)
+        chosen = chosen.clone()
+        chosen[i] = raw
+        out[i] = chosen
+    return out
+
+
+def cross_similarity_hard_mining(sd, text_seq, text_mask, vis_all, vis_mask_all, chosen, heads):
+    """_cross_similarity_hard_mining (univl_video_ret.py:91-144) given the selection matrix `chosen` [bsz, bsz]
+    (hard_mining_indices): entry [i, j] scores local text i against gathered video chosen[i, j]."""
+    bsz = text_seq.shape[0]
+    ti = torch.arange(bsz).repeat_interleave(bsz)
+    vi = chosen.reshape(-1)
+    return cross_pair_logits(sd, text_seq[ti], text_mask[ti], vis_all[vi], vis_mask_all[vi], heads).view(bsz, bsz)
+
+
+def hard_mining_weights(l1_diag, method="top_k"):
+    """Row re-weighting of forward_stage2 with re_weight_method == 'median' (univl_video_ret.py:414-430): rows whose level-1
+    positive score is above the batch MEAN (named 'median' in the reference) get max((mean − min)/(d − min), 0.2), others 1.
+    With re_sample_method 'top_k' the reference reads the diagonal AFTER _cross_similarity_hard_mining subtracted 100 from it in
+    place (:113, through the row view of the detached clone); the formula is shift-invariant up to fp32 rounding, and the shift
+    is reproduced here so that the weights are bit-identical."""
+    if method == "top_k":
+        l1_diag = l1_diag - 100.0
+    mean, mn = l1_diag.mean(), l1_diag.min()
+    w = torch.ones_like(l1_diag)
+    above = l1_diag > mean
+    w[above] = torch.clamp_min((mean - mn) / (l1_diag[above] - mn), 0.2)
+    return w
+
+
+def mil_nce_matrix(S, weight=None):
+    """get_mil_nce_loss (univl_video_ret.py:146-197) on an explicit square score matrix (n_pair 1) with the optional row weights:
+    mean_j w_j · ( LSE( {S[i, j] ∀i} ∪ {S[j, k], k ≠ j} ) − S[j, j] )."""
+    B = S.shape[0]
+    eye = torch.eye(B, dtype=torch.bool, device=S.device)
+    both = torch.cat([S.t(), S.masked_fill(eye, float("-inf"))], dim=1)
+    per_row = torch.logsumexp(both, dim=1) - torch.diagonal(S)
+    return (per_row * weight).mean() if weight is not None else per_row.mean()

@@ -162,6 +162,42 @@ def im2row(img, p, Kp):
     return out.reshape(-1, Kp)
 
 
+def gather_rows(src, ids):
+    ok = (ids >= 0) & (ids < src.shape[0])
+    out = src[ids.clamp(0, src.shape[0] - 1)].clone()
+    out[~ok] = 0
+    return out
+
+
+def relu_fwd(x):
+    return torch.relu(x)
+
+
+def relu_bwd(dy, x):
+    return dy * (x > 0).to(dy.dtype)
+
+
+def _mil_parts(S, w):
+    B = S.shape[0]
+    eye = torch.eye(B, dtype=torch.bool)
+    both = torch.cat([S.t(), S.masked_fill(eye, float("-inf"))], dim=1)
+    lse = torch.logsumexp(both, dim=1)
+    ww = torch.ones(B) if w is None else w
+    return lse, (ww * (lse - torch.diagonal(S))).sum()
+
+
+def mil_nce_matrix_fwd(S, w=None):
+    return _mil_parts(S.float(), w)
+
+
+def mil_nce_matrix_bwd(S, w, lse, gout):
+    with torch.enable_grad():
+        x = S.float().detach().requires_grad_()
+        _, total = _mil_parts(x, w)
+        (g,) = torch.autograd.grad(total / S.shape[0], x)
+    return g * gout
+
+
 @contextlib.contextmanager
 def patched():
     """Swaps the kernel wrappers of b200mm.ops for the stand-ins above (restored on exit)."""

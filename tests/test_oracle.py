@@ -176,3 +176,46 @@ def test_restated_m2_encoder_matches_golden_forward_backward(golden_dir):
     for n, v in sd.items():
         if torch.is_floating_point(v) and n not in fx["grads"]:
             assert v.grad is None or float(v.grad.abs().max()) == 0.0, n
+
+
+def test_restated_stage2_cross_similarity_and_hard_mining_match_golden(golden_dir):
+    """Stage-2 restatements vs the unmodified reference functions (oracle/make_golden.py::make_stage2): blockwise N x M scores,
+    hard-negative selection (index-exact), the 'median' row weights, the weighted MIL-NCE on the score matrix, and all gradients."""
+    fx = _load(golden_dir, "stage2.pt")
+    heads = fx["config"]["heads"]
+
+    def fresh():
+        return {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+
+    c = fx["cross"]
+    sd = fresh()
+    seq, vis = c["seq"].clone().requires_grad_(), c["vis"].clone().requires_grad_()
+    logits = restated.cross_similarity(sd, seq, c["am"], vis, c["vm"], heads)
+    torch.testing.assert_close(logits, c["logits"], rtol=1e-4, atol=1e-5)
+    logits.square().sum().backward()
+    torch.testing.assert_close(seq.grad, c["d_seq"], rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(vis.grad, c["d_vis"], rtol=1e-3, atol=1e-6)
+    for n, g in c["grads"].items():
+        assert float((sd[n].grad - g).abs().max() / g.abs().max().clamp_min(1e-4)) < 3e-4, n  # key.bias grads are analytically 0
+
+    for method in ["top_k", "nearliest"]:
+        h = fx["hard_" + method]
+        B = h["seq"].shape[0]
+        sd = fresh()
+        seq, vis = h["seq"].clone().requires_grad_(), h["vis"].clone().requires_grad_()
+        l1_before = h["l1"].clone()
+        chosen = restated.hard_mining_indices(h["l1"], 0, B, method)
+        assert torch.equal(h["l1"], l1_before)  # not modified
+        assert torch.equal(torch.diagonal(chosen), torch.arange(B))  # slot i = the positive
+        l2 = restated.cross_similarity_hard_mining(sd, seq, h["am"], vis, h["vm"], chosen, heads)
+        torch.testing.assert_close(l2, h["logits"], rtol=1e-4, atol=1e-5)
+        w = restated.hard_mining_weights(torch.diagonal(h["l1"]), method)
+        assert torch.equal(w, h["weights"])
+        torch.testing.assert_close(restated.mil_nce_matrix(l2), h["loss_unweighted"], rtol=1e-5, atol=1e-6)
+        loss = restated.mil_nce_matrix(l2, w)
+        torch.testing.assert_close(loss, h["loss"], rtol=1e-5, atol=1e-6)
+        loss.backward()
+        torch.testing.assert_close(seq.grad, h["d_seq"], rtol=1e-3, atol=1e-7)
+        torch.testing.assert_close(vis.grad, h["d_vis"], rtol=1e-3, atol=1e-7)
+        for n, g in h["grads"].items():
+            assert float((sd[n].grad - g).abs().max() / g.abs().max().clamp_min(1e-3)) < 3e-4, (method, n)  # the last bias has an analytically zero gradient (shift invariance)
