@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace b200mm {
 
@@ -40,6 +41,24 @@ __device__ __forceinline__ float sl_dact(float x) {
   return ACT == B200MM_ACT_QUICKGELU ? dact_quickgelu(x) : (ACT == B200MM_ACT_GELU_ERF ? dact_gelu_erf(x) : 1.f);
 }
 
+// act(x) and act'(x) together: QuickGELU shares the sigmoid, erf-GELU the Gaussian cdf / pdf pair
+template <int ACT>
+__device__ __forceinline__ void sl_act_dact(float x, float& a, float& d) {
+  if (ACT == B200MM_ACT_QUICKGELU) {
+    const float s = sigmoid_1702(x);
+    a = x * s;
+    d = s * fmaf(1.702f * x, 1.f - s, 1.f);
+  } else if (ACT == B200MM_ACT_GELU_ERF) {
+    float cdf, expo;
+    gauss_cdf_pdf(x, cdf, expo);
+    a = x * cdf;
+    d = fmaf(x * 0.3989422804014327f, expo, cdf);
+  } else {
+    a = x;
+    d = 1.f;
+  }
+}
+
 // CTA-wide sum through one smem slot per warp; `red` must not be reused before the NEXT __syncthreads of the caller
 template <int THREADS>
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -53,8 +72,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // thread t, slot i covers columns (i*THREADS + t)*8 .. +7
-template <int VPT, int THREADS, int ACT>
-__global__ void __launch_bounds__(THREADS) act_ln_fwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ w,
+template <int VPT, int THREADS, int ACT, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) act_ln_fwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ w,
                                                              const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int32_t W,
                                                              float eps) {
@@ -122,8 +141,8 @@ __global__ void __launch_bounds__(THREADS) act_ln_fwd_kernel(const __nv_bfloat16
   }
 }
 
-template <int VPT, int THREADS, int ACT>
-__global__ void __launch_bounds__(THREADS) act_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
+template <int VPT, int THREADS, int ACT, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) act_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
                                                              const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                              const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ du,
                                                              float* __restrict__ dw, float* __restrict__ db, int64_t rows, int32_t W) {
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(THREADS) act_ln_bwd_kernel(const __nv_bfloat16
       }
     }
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[VPT][8], gy[VPT][8];
+    float xh[VPT][8], gy[VPT][8], da[VPT][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
@@ -163,7 +182,9 @@ __global__ void __launch_bounds__(THREADS) act_ln_bwd_kernel(const __nv_bfloat16
       sl_unpack8(wq[i], wv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xh[i][j] = (sl_act<ACT>(uv[j]) - mean) * rstd;
+        float g;
+        sl_act_dact<ACT>(uv[j], g, da[i][j]);  // act(u) and act'(u) from ONE evaluation of the shared sub-expressions
+        xh[i][j] = (g - mean) * rstd;
         gy[i][j] = dyv[j] * wv[j];  // dy and w are zero in padding slots, so those add nothing below
         s1 += gy[i][j];
         s2 = fmaf(gy[i][j], xh[i][j], s2);
@@ -193,15 +214,8 @@ __global__ void __launch_bounds__(THREADS) act_ln_bwd_kernel(const __nv_bfloat16
       const int col = (i * THREADS + threadIdx.x) * 8;
       if (col < W) {
         float o[8];
-        if (ACT != B200MM_ACT_NONE) {
-          float uv[8];
-          sl_unpack8(uq[i], uv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rstd * fmaf(-xh[i][j], s2, gy[i][j] - s1) * sl_dact<ACT>(uv[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rstd * fmaf(-xh[i][j], s2, gy[i][j] - s1);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = rstd * fmaf(-xh[i][j], s2, gy[i][j] - s1) * da[i][j];
         *reinterpret_cast<uint4*>(du + off + col) = sl_pack8(o);
       }
     }
@@ -238,34 +252,52 @@ using namespace b200mm;
 
 namespace {
 
+// launch shape: THREADS x VPT vectors cover the row. Defaults measured on B200 (tools/subln_bench.py); B200MM_SUBLN_FWD / _BWD =
+// "<threads>,<ctas_per_sm>" override them for bring-up sweeps.
+struct SubLnCfg { int threads, per_sm; };
+static SubLnCfg subln_cfg(const char* env, int def_threads, int def_per_sm) {
+  SubLnCfg c{def_threads, def_per_sm};
+  if (const char* e = getenv(env)) {
+    int t = 0, p = 0;
+    if (sscanf(e, "%d,%d", &t, &p) == 2 && (t == 128 || t == 256 || t == 512) && p > 0 && p <= 32) c = SubLnCfg{t, p};
+  }
+  return c;
+}
+
 template <int ACT>
 int sub_ln_fwd(const __nv_bfloat16* u, const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* y, float* mean, float* rstd, int64_t rows,
                int32_t W, float eps, cudaStream_t st) {
-  const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(sm_count()) * 8));
-  const int v = static_cast<int>(ceil_div(W, 1024));  // 128 threads x 8 columns per slot
-  switch (v) {
-    case 1: act_ln_fwd_kernel<1, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
-    case 2: act_ln_fwd_kernel<2, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
-    case 3: act_ln_fwd_kernel<3, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
-    case 4: act_ln_fwd_kernel<4, 128, ACT><<<grid, 128, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps); break;
-    default:
-      if (W <= 8192) act_ln_fwd_kernel<4, 256, ACT><<<grid, 256, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps);
-      else { set_last_error("act_layernorm_fwd: width %d not supported (max 8192)", W); return B200MM_ERR_SHAPE; }
-  }
+  SubLnCfg c = subln_cfg("B200MM_SUBLN_FWD", W <= 4096 ? 128 : 256, 8);
+  if (ceil_div(W, c.threads * 8) > (c.threads == 512 ? 2 : 4)) c.threads = W <= 4096 ? 128 : 256;  // override does not fit this width
+  B200MM_REQUIRE(W <= 8192, B200MM_ERR_SHAPE, "act_layernorm_fwd: width %d not supported (max 8192)", W);
+  const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(sm_count()) * c.per_sm));
+  const int v = static_cast<int>(ceil_div(W, c.threads * 8));
+#define SL_F(V, T, MB) act_ln_fwd_kernel<V, T, ACT, MB><<<grid, T, 0, st>>>(u, w, b, y, mean, rstd, rows, W, eps)
+  if (c.threads == 128) { if (v == 1) SL_F(1, 128, 1); else if (v == 2) SL_F(2, 128, 1); else if (v == 3) SL_F(3, 128, 1); else SL_F(4, 128, 1); }
+  else if (c.threads == 256) { if (v == 1) SL_F(1, 256, 1); else if (v == 2) SL_F(2, 256, 1); else if (v == 3) SL_F(3, 256, 1); else SL_F(4, 256, 1); }
+  else { if (v == 1) SL_F(1, 512, 2); else SL_F(2, 512, 1); }
+#undef SL_F
   return check_launch("act_ln_fwd_kernel");
 }
 
 template <int ACT>
 int sub_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* u, const float* mean, const float* rstd, const __nv_bfloat16* w, __nv_bfloat16* du,
                float* dw, float* db, int64_t rows, int32_t W, cudaStream_t st) {
-  // each CTA ends with 2·W atomics: keep the CTA count at a few per SM
-  const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(sm_count()) * 4));
-  // register budget: 2 accumulators + xhat + dy*w per column held by the thread -> at most 32 columns per thread below 8192
-  if (W <= 1024) act_ln_bwd_kernel<1, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
-  else if (W <= 2048) act_ln_bwd_kernel<2, 128, ACT><<<grid, 128, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
-  else if (W <= 4096) act_ln_bwd_kernel<2, 256, ACT><<<grid, 256, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
-  else if (W <= 8192) act_ln_bwd_kernel<4, 256, ACT><<<grid, 256, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W);
-  else { set_last_error("act_layernorm_bwd: width %d not supported (max 8192)", W); return B200MM_ERR_SHAPE; }
+  // register budget: 2 accumulators + xhat + dy*w + act' per column held by the thread -> at most 16 columns per thread up to 4096
+  // (32 up to 8192); each CTA ends with 2*W atomics, so the CTA count stays at a few per SM
+  // measured at 100 864 x 4096 (profiles/r01e_subln_sweep.log): with an activation the kernel is MUFU/issue-bound and wants the most
+  // warps (512 threads, 2 CTAs/SM: 0.77 ms vs 1.30 ms at 256 threads); without one 256 threads x 2 CTAs/SM is best (68 % of HBM peak)
+  const int def_threads = W <= 2048 ? 128 : (ACT != B200MM_ACT_NONE ? 512 : 256);
+  SubLnCfg c = subln_cfg("B200MM_SUBLN_BWD", def_threads, W <= 2048 ? 4 : 2);
+  if (ceil_div(W, c.threads * 8) > (c.threads == 512 ? 2 : (c.threads == 256 ? 4 : 2))) c.threads = W <= 2048 ? 128 : 256;
+  B200MM_REQUIRE(W <= 8192, B200MM_ERR_SHAPE, "act_layernorm_bwd: width %d not supported (max 8192)", W);
+  const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(sm_count()) * c.per_sm));
+  const int v = static_cast<int>(ceil_div(W, c.threads * 8));
+#define SL_B(V, T, MB) act_ln_bwd_kernel<V, T, ACT, MB><<<grid, T, 0, st>>>(dy, u, mean, rstd, w, du, dw, db, rows, W)
+  if (c.threads == 128) { if (v == 1) SL_B(1, 128, 1); else SL_B(2, 128, 1); }
+  else if (c.threads == 256) { if (v == 1) SL_B(1, 256, 1); else if (v == 2) SL_B(2, 256, 1); else SL_B(4, 256, 1); }
+  else { if (v == 1) SL_B(1, 512, 2); else SL_B(2, 512, 1); }
+#undef SL_B
   return check_launch("act_ln_bwd_kernel");
 }
 

@@ -87,7 +87,7 @@ def test_cross_similarity_matches_reference_golden(golden_dir, max_pairs):
     assert rel_l2(seq.grad, o_seq.grad) < 4e-2 and rel_l2(vis.grad, o_vis.grad) < 4e-2
     got = param_grads(sc)
     for n, p in sd.items():
-        if float(p.grad.abs().max()) < 1e-4:
+        if p.grad is None or float(p.grad.abs().max()) < 1e-4:
             continue
         assert rel_l2(got[n], p.grad) < 5e-2, (n, rel_l2(got[n], p.grad))
 
@@ -106,7 +106,8 @@ def test_hard_mining_matches_reference_golden(golden_dir, method):
     # topk(sorted=False) is device-defined in the reference itself); weights bit-identical
     ref_chosen = restated.hard_mining_indices(h["l1"], 0, B, method)
     assert torch.equal(torch.diagonal(chosen).cpu(), torch.arange(B))
-    assert torch.equal(hard_mining_weights(torch.diagonal(l1), method).cpu(), h["weights"])
+    # bit-identical on the same device (tests/test_cross_host_cpu.py); CUDA's mean() reduces in another order than the CPU golden run
+    torch.testing.assert_close(hard_mining_weights(torch.diagonal(l1), method).cpu(), h["weights"], rtol=2e-6, atol=1e-7)
     sc = build_scorer(fx).cuda().to(BF).train()
     seq, vis = h["seq"].to(BF).cuda().requires_grad_(), h["vis"].to(BF).cuda().requires_grad_()
     l2 = sc.cross_similarity_hard_mining((vis, h["vm"].cuda(), None, 1, None), (seq, h["am"].cuda(), None, B, None), l1.clone(), method)
@@ -172,9 +173,16 @@ def test_cross_scorer_hd64_blocks_match_oracle():
     assert rel_l2(logits, o_logits) < 1.5e-2, rel_l2(logits, o_logits)
     logits.square().sum().backward()
     o_logits.square().sum().backward()
-    assert rel_l2(a.grad, o_a.grad) < 4e-2 and rel_l2(b.grad, o_b.grad) < 4e-2
+    # calibrator: the same oracle arithmetic in bf16 torch eager on the GPU (what the reference modules do after .cuda().bfloat16()).
+    # The visual-token gradient is ~1e-3 of the text-token gradient here (9 of 86 keys, reached through attention only) and is a sum
+    # over 12 pairs of terms of either sign: its bf16 noise floor is far above the 2^-9 of well-conditioned tensors.
+    sdb = {k: v.detach().to(BF).cuda().requires_grad_() for k, v in sd.items()}
+    e_a, e_b = seq.cuda().requires_grad_(), vis.cuda().requires_grad_()
+    restated.cross_similarity(sdb, e_a, am.cuda(), e_b, vm.cuda(), heads).float().square().sum().backward()
+    assert rel_l2(a.grad, o_a.grad) < max(4e-2, 2.0 * rel_l2(e_a.grad, o_a.grad))
+    assert rel_l2(b.grad, o_b.grad) < max(4e-2, 2.0 * rel_l2(e_b.grad, o_b.grad)), (rel_l2(b.grad, o_b.grad), rel_l2(e_b.grad, o_b.grad))
     got = param_grads(sc)
     for n, p in sd.items():
-        if float(p.grad.abs().max()) < 1e-4:
+        if p.grad is None or float(p.grad.abs().max()) < 1e-4:
             continue
-        assert rel_l2(got[n], p.grad) < 5e-2, (n, rel_l2(got[n], p.grad))
+        assert rel_l2(got[n], p.grad) < max(5e-2, 2.0 * rel_l2(sdb[n].grad, p.grad)), (n, rel_l2(got[n], p.grad))

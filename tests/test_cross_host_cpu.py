@@ -15,7 +15,7 @@ BF = torch.bfloat16
 
 
 def rel_l2(got, ref):
-    got, ref = got.detach().float(), ref.detach().float()
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
     return float((got - ref).norm() / ref.norm().clamp_min(1e-12))
 
 
