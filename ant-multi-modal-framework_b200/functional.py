@@ -345,7 +345,7 @@ def _m2_layer_forward(x, p, key_bias, B, L, H, eps):
     del h2
     g_n, mean_f, rstd_f = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)  # ffn_layernorm(gelu(u)) in one pass
     y = ops.gemm(g_n, fc2_w, bias=fc2_b, residual=x_mid)
-    return y, (mean1, rstd1, qkv, a, lse, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f)
+    return y, (mean1, rstd1, qkv, a, lse, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f), g_n
 
 
 class M2EncoderLayerFn(Function):
@@ -353,29 +353,35 @@ class M2EncoderLayerFn(Function):
 
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, q_w, q_b, k_w, k_b, v_w, v_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b,
-                fc2_w, fc2_b, key_bias, B, L, H, eps, checkpoint):
+                fc2_w, fc2_b, key_bias, B, L, H, eps, checkpoint, keep_act):
         qkv_w = torch.cat([q_w, k_w, v_w], dim=0)
         qkv_b = torch.cat([q_b, k_b, v_b], dim=0)
         p = (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b)
-        y, saved = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
-        ctx.meta = (B, L, H, eps, checkpoint, key_bias is not None)
+        y, saved, g_n = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+        keep_act = bool(keep_act) and not checkpoint
+        ctx.meta = (B, L, H, eps, checkpoint, key_bias is not None, keep_act)
         kb = (key_bias,) if key_bias is not None else ()
         if checkpoint:
             ctx.save_for_backward(x, *p, *kb)
+        elif keep_act:  # memory for time: the normalised FFN hidden (4W per token) is kept instead of re-running gelu + sub-LN
+            ctx.save_for_backward(x, *p, *kb, *saved, g_n)
         else:
             ctx.save_for_backward(x, *p, *kb, *saved)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        B, L, H, eps, checkpoint, has_kb = ctx.meta
+        B, L, H, eps, checkpoint, has_kb, keep_act = ctx.meta
         t = ctx.saved_tensors
         x, p = t[0], t[1:17]
         key_bias = t[17] if has_kb else None
         rest = t[17 + int(has_kb):]
         (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b) = p
+        g_n = None
         if checkpoint:
-            _, rest = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+            _, rest, g_n = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+        elif keep_act:
+            rest, g_n = rest[:-1], rest[-1]
         mean1, rstd1, qkv, a, lse, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f = rest
         W = x.shape[1]
         F_ = fc1_w.shape[0]
@@ -383,7 +389,8 @@ class M2EncoderLayerFn(Function):
         # ln1 w,b | qkv_b | iln w,b | o_b | ln2 w,b | fc1_b | fln w,b | fc2_b
         vg = _VecGrads(x.device, [W, W, 3 * W, W, W, W, W, W, F_, F_, F_, W])
         # ---- FFN branch: fc2(ffn_ln(gelu(fc1 h2)))
-        g_n, _, _ = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)  # recomputed, never kept
+        if g_n is None:
+            g_n, _, _ = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)  # recomputed unless the keep-activation policy kept it
         d_fc2_w = _wgrad(dy, g_n)
         del g_n
         ops.rowsum_periodic(dy, vg[11])
@@ -419,7 +426,7 @@ class M2EncoderLayerFn(Function):
         dq_w, dk_w, dv_w = d_qkv_w[:W], d_qkv_w[W: 2 * W], d_qkv_w[2 * W:]
         dq_b, dk_b, dv_b = d_qkv_b[:W], d_qkv_b[W: 2 * W], d_qkv_b[2 * W:]
         return (dx, d_ln1_w, d_ln1_b, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_iln_w, d_iln_b, d_o_w, d_o_b, d_ln2_w, d_ln2_b, d_fc1_w, d_fc1_b,
-                d_fln_w, d_fln_b, d_fc2_w, d_fc2_b, None, None, None, None, None, None)
+                d_fln_w, d_fln_b, d_fc2_w, d_fc2_b, None, None, None, None, None, None, None)
 
 
 class LayerNormFn(Function):

@@ -84,6 +84,7 @@ class EncoderLayer(nn.Module):
         self.ffn = MultiwayNetwork(lambda: FeedForwardNetwork(embed_dim, ffn_dim, eps))
         self.final_layer_norm = MultiwayNetwork(lambda: nn.LayerNorm(embed_dim, eps=eps))
         self.checkpoint = False
+        self.keep_act = False
 
     def layer_params(self, sp):
         a = self.self_attn
@@ -95,7 +96,7 @@ class EncoderLayer(nn.Module):
 
     def forward_tokens(self, x2d, key_bias, B, L, split_position):
         return Fn.M2EncoderLayerFn.apply(x2d, *self.layer_params(split_position), key_bias, B, L, self.self_attn.num_heads, self.eps,
-                                         self.checkpoint)
+                                         self.checkpoint, self.keep_act)
 
 
 class PositionalEmbedding(nn.Embedding):
@@ -133,6 +134,12 @@ class Encoder(nn.Module):
     def set_grad_checkpointing(self, enable=True):
         for layer in self.layers:
             layer.checkpoint = bool(enable)
+
+    def set_keep_activation(self, n_layers):
+        """Keep the sub-LN-normalised FFN hidden (4·W per token) of the first `n_layers` layers for backward instead of
+        recomputing gelu + sub-LN from the pre-activation (memory for time)."""
+        for i, layer in enumerate(self.layers):
+            layer.keep_act = i < n_layers
 
     def forward_tokens(self, x2d, B, L, split_position, drop=None, key_bias=None, mask_input=True):
         """x2d: [B*L, W] token embeddings with positions added; drop: uint8 [B*L] (1 = padded row) or None."""
@@ -274,6 +281,12 @@ class M2Encoder(nn.Module):
         self.backbone.encoder.set_grad_checkpointing(enable)
         if self.use_vl:
             self.backbone_vl.set_grad_checkpointing(enable)
+
+    def set_keep_activation(self, n_layers):
+        n0 = len(self.backbone.encoder.layers)
+        self.backbone.encoder.set_keep_activation(n_layers)
+        if self.use_vl:
+            self.backbone_vl.set_keep_activation(max(0, n_layers - n0))
 
     def _heads(self, h, hv, B, L, proj, proj_vl):
         f = Fn.RowNormFn.apply(Fn.ClsLinearFn.apply(h, _bf16(proj.fc.weight), B, L))

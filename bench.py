@@ -129,6 +129,8 @@ def build_model(name, device, ckpt_every, keep_act=0):
         m2 = M2Encoder(**cfg).to(device).to(torch.bfloat16).train()
         if ckpt_every > 0:
             m2.set_grad_checkpointing(True)
+        if keep_act > 0:
+            m2.set_keep_activation(keep_act)
         return _M2Step(m2), dict(image_resolution=cfg["image_size"], vocab_size=cfg["vocab_size"], vision_layers=cfg["encoder_layers"])
 
     cfg = dict(CONFIGS[name])

@@ -72,7 +72,7 @@ def test_mask_rows_is_exact():
     assert torch.equal(ops.mask_rows(x.clone(), drop, inplace=True), y)
 
 
-def _build(fx, checkpoint=False):
+def _build(fx, checkpoint=False, keep=0):
     from b200mm.modules import M2Encoder
 
     c = fx["config"]
@@ -82,6 +82,7 @@ def _build(fx, checkpoint=False):
     assert not unexpected and all(k.startswith(("norm.", "pooler.")) for k in missing)
     m = m.cuda().to(BF).train()
     m.set_grad_checkpointing(checkpoint)
+    m.set_keep_activation(keep)
     return m
 
 
@@ -142,11 +143,11 @@ def _check_against(m, fx_sd, image, ids, masks, heads, golden=None):
     assert med < max(2.5e-2, 2.0 * med_eager), (med, med_eager)
 
 
-@pytest.mark.parametrize("checkpoint", [False, True])
-def test_m2_encoder_matches_reference_golden(golden_dir, checkpoint):
+@pytest.mark.parametrize("checkpoint,keep", [(False, 0), (True, 0), (False, 3)])
+def test_m2_encoder_matches_reference_golden(golden_dir, checkpoint, keep):
     """hd 32 (mma.sync attention path), L 17 / 12, width 64: the golden vectors of the unmodified reference classes."""
     fx = torch.load(os.path.join(golden_dir, "m2_tiny.pt"), weights_only=False)
-    m = _build(fx, checkpoint)
+    m = _build(fx, checkpoint, keep)
     _check_against(m, fx["state_dict"], fx["image"], fx["ids"], fx["masks"], fx["config"]["heads"], golden=fx)
 
 

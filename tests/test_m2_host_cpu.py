@@ -17,8 +17,8 @@ def rel_l2(got, ref):
     return float((got - ref).norm() / ref.norm().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("checkpoint", [False, True])
-def test_m2_glue_reproduces_reference_golden(golden_dir, checkpoint):
+@pytest.mark.parametrize("checkpoint,keep", [(False, 0), (True, 0), (False, 2)])
+def test_m2_glue_reproduces_reference_golden(golden_dir, checkpoint, keep):
     from b200mm.modules import M2Encoder
     from oracle import restated
 
@@ -29,6 +29,7 @@ def test_m2_glue_reproduces_reference_golden(golden_dir, checkpoint):
     m.load_state_dict(fx["state_dict"], strict=False)
     m = m.to(BF).train()
     m.set_grad_checkpointing(checkpoint)
+    m.set_keep_activation(keep)
     with emulated_ops.patched():
         img = m.infer_image({"image": [fx["image"]]})
         txt = m.infer_text({"text_ids": fx["ids"], "text_masks": fx["masks"]})
