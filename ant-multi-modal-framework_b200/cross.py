@@ -133,15 +133,14 @@ def hard_mining_weights(l1_diag, method="top_k"):
     return torch.where(d > mean, torch.clamp_min((mean - mn) / (d - mn), 0.2), torch.ones_like(d))
 
 
-class CrossScorer(nn.Module):
-    """Scores (text, video) pairs with the cross encoder of `text_encoder` (a B200RobertBertEncoder: `.encoder` = BertEncoder whose
-    layers are shared with the text tower, `.text_projection`; univl_video_base.py:47-54, arch 'clip') and owns `similarity_dense`
-    under the reference's parameter names (similarity_dense.0.*, similarity_dense.2.*)."""
+class PairScorer:
+    """The scoring logic, holding REFERENCES to the modules it runs through (not an nn.Module: the owner keeps the parameters under the
+    reference's names): `text_encoder` = a B200RobertBertEncoder-like object (`.encoder.layer[i].forward_tokens`, `.text_projection`),
+    `similarity_dense` = nn.Sequential(Linear, ReLU, Linear) used as a parameter container."""
 
-    def __init__(self, text_encoder, out_dim, max_pairs=8192):
-        super().__init__()
+    def __init__(self, text_encoder, similarity_dense, max_pairs=8192):
         self.text_encoder = text_encoder
-        self.similarity_dense = nn.Sequential(nn.Linear(out_dim, out_dim * 2), nn.ReLU(True), nn.Linear(out_dim * 2, 1))
+        self.similarity_dense = similarity_dense
         self.max_pairs = max_pairs
 
     # ---- one block of aligned pairs -------------------------------------------------------------------------------------
@@ -209,3 +208,30 @@ class CrossScorer(nn.Module):
             B = l2_simi.shape[0]
             w = hard_mining_weights(torch.diagonal(l1_simi_matrix[beg_idx: beg_idx + B, beg_idx: beg_idx + B]), re_sample_method)
         return mil_nce_matrix_loss(l2_simi, w)
+
+
+class CrossScorer(nn.Module):
+    """Stand-alone owner: scores (text, video) pairs with the cross encoder of `text_encoder` (a B200RobertBertEncoder: `.encoder` =
+    BertEncoder whose layers are shared with the text tower, `.text_projection`; univl_video_base.py:47-54, arch 'clip') and owns
+    `similarity_dense` under the reference's parameter names (similarity_dense.0.*, similarity_dense.2.*)."""
+
+    def __init__(self, text_encoder, out_dim, max_pairs=8192):
+        super().__init__()
+        self.text_encoder = text_encoder
+        self.similarity_dense = nn.Sequential(nn.Linear(out_dim, out_dim * 2), nn.ReLU(True), nn.Linear(out_dim * 2, 1))
+        self.max_pairs = max_pairs
+
+    def _scorer(self):
+        return PairScorer(self.text_encoder, self.similarity_dense, self.max_pairs)
+
+    def score_pair_list(self, *a, **k):
+        return self._scorer().score_pair_list(*a, **k)
+
+    def cross_similarity(self, *a, **k):
+        return self._scorer().cross_similarity(*a, **k)
+
+    def cross_similarity_hard_mining(self, *a, **k):
+        return self._scorer().cross_similarity_hard_mining(*a, **k)
+
+    def level2_loss(self, *a, **k):
+        return self._scorer().level2_loss(*a, **k)

@@ -106,6 +106,30 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+VTP_FRAMES = 8
+
+
+class _VtpStep(torch.nn.Module):
+    """BASELINE.json configs[3] geometry: base_vtp video-text retrieval (arch 'clip'), ViT-B/16 over 8 frames + BERT-base, level-1 MIL-NCE +
+    level-2 cross-modal scoring with hard-negative mining ('top_k') and 'median' row weights — one training forward of
+    b200mm.vtp.B200VideoTextRetrieval behind the (frames, text) -> loss interface of the bench."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.m = model
+
+    def contrastive_loss(self, image, text, group=None):
+        B = text.shape[0]
+        F_ = image.shape[0] // B
+        img_input = dict(image_data=image.view(B, F_, *image.shape[1:]),
+                         image_pad_mask=torch.zeros((B, F_) + tuple(image.shape[2:]), dtype=torch.bool, device=image.device),  # "no padding"
+                         image_n_clips=[1] * B, image_num_frames=[F_] * B)
+        mask = (text != 0).long()
+        caption = dict(caption_raw_input_ids=text, caption_input_ids=text, caption_input_mask=mask)
+        out = self.m(img_input, caption)
+        return out["losses"]["level1_similarity_loss"] + out["losses"]["level2_similarity_loss"]
+
+
 class _M2Step(torch.nn.Module):
     """M2-Encoder ITC step behind the (image, text) -> loss interface of the bench: text_masks = ids != [PAD]."""
 
@@ -123,6 +147,24 @@ class _M2Step(torch.nn.Module):
 def build_model(name, device, ckpt_every, keep_act=0):
     from b200mm.modules import CNCLIP, CONFIGS, M2_CONFIGS, M2Encoder
 
+    if name == "base_vtp-ViT-B-16":
+        from b200mm import vtp
+
+        c = dict(CONFIGS["ViT-B-16"])
+        vcfg = dict(training_stage="stage1+stage2", arch_type="clip", hidden_size=c["text_hidden_size"], with_moco=False,
+                    hard_example_mining=True, re_sample_method="top_k", re_weight_method="median",
+                    image_encoder=dict(type="B200VitImageEncoder", params=dict(
+                        model_name="-", input_resolution=c["image_resolution"], patch_size=c["vision_patch_size"], width=c["vision_width"],
+                        layers=c["vision_layers"], out_dim=c["embed_dim"], pretrained=False)),
+                    text_encoder=dict(type="B200RobertBertEncoder", params=dict(
+                        pretrained=False, hidden_size=c["text_hidden_size"], intermediate_size=c["text_intermediate_size"],
+                        num_hidden_layers=c["text_num_hidden_layers"], num_attention_heads=c["text_num_attention_heads"],
+                        vocab_size=c["vocab_size"], max_position_embeddings=c["text_max_position_embeddings"],
+                        out_dim=c["text_hidden_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)))
+        torch.manual_seed(0)
+        m = vtp.B200VideoTextRetrieval(vcfg).to(device).to(torch.bfloat16).train()
+        return _VtpStep(m), dict(image_resolution=c["image_resolution"], vocab_size=c["vocab_size"], vision_layers=c["vision_layers"],
+                                 frames=VTP_FRAMES)
     if name in M2_CONFIGS:
         cfg = dict(M2_CONFIGS[name])
         torch.manual_seed(0)
@@ -181,7 +223,8 @@ def run_ours(args):
     if world > 1 and args.micro_batch == 0:
         step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                              static_graph=True)
-    image_h, text_h = synth_batch(B, res, L, cfg["vocab_size"], 1234 + rank)
+    image_h, text_h = synth_batch(B * cfg.get("frames", 1), res, L, cfg["vocab_size"], 1234 + rank)
+    text_h = text_h[:B].contiguous()
     image_h = image_h.to(torch.bfloat16).pin_memory()
     text_h = text_h.pin_memory()
     image_d, text_d = image_h.to(device), text_h.to(device)
@@ -276,12 +319,20 @@ def run_ours(args):
     out = None
     if rank == 0:
         fpp = FLOP_PER_PAIR.get(args.model)
+        if args.model.startswith("base_vtp"):
+            # per pair, fwd+bwd = 3 x (8 frames of ViT-B/16 + BERT-base at L + B cross-encoder passes over L + 2 tokens): hard mining scores every
+            # text against B videos, so the cross-encoder work per pair grows with the per-GPU batch
+            w = 768
+            fpp = 3.0 * (VTP_FRAMES * 35.1e9 + (24 * w * w + 4 * L * w) * 12 * L + B * (24 * w * w + 4 * (L + 2) * w) * 12 * (L + 2))
         out = {
             "metric": METRIC, "value": round(pairs_per_s, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (seeded N(0,1) images, random ids with [CLS]/[SEP]/[PAD]; random-init weights, reference init)",
             "config": {"workload": (f"BASELINE.json configs[{1 if world == 1 else 2}]: CNCLIP {args.model} + BERT-base, fwd + fused contrastive loss + bwd"
-                                    if args.model in FLOP_PER_PAIR and not args.model.startswith("M2") else
+                                    if args.model in FLOP_PER_PAIR and not args.model.startswith(("M2", "base_vtp")) else
+                                    (f"BASELINE.json configs[3] geometry: base_vtp video-text (arch clip) ViT-B/16 x {VTP_FRAMES} frames + BERT-base, level-1 MIL-NCE + "
+                                     f"level-2 cross-modal scoring of B x B mined pairs (86-token sequences) + weighted MIL-NCE, fwd + bwd; {B} pairs per GPU")
+                                    if args.model.startswith("base_vtp") else
                                     f"prj/M2_Encoder {args.model} (BEiT-3 multiway): infer_image + infer_text + symmetric ITC on both head pairs, fwd + bwd"),
                        "model": args.model, "per_gpu_batch": B, "global_batch": B * world, "image_res": res, "seq_len": L,
                        "parallelism": f"dp{world}" + (" + embedding all-gather / grad reduce-scatter, DDP grad all-reduce in the timed region" if world > 1 else ""),

@@ -162,6 +162,23 @@ def im2row(img, p, Kp):
     return out.reshape(-1, Kp)
 
 
+def masked_mean_fwd(x, pad):
+    R, P, W = x.shape
+    if pad is None:
+        inv = torch.full((R,), 1.0 / P)
+        return (x.float().mean(1)).to(BF), inv, None
+    pad8 = pad.to(torch.uint8)
+    keep = (pad8 == 0).float()
+    inv = 1.0 / keep.sum(1)
+    return ((x.float() * keep[:, :, None]).sum(1) * inv[:, None]).to(BF), inv, pad8
+
+
+def masked_mean_bwd(dy, pad, inv, P):
+    R, W = dy.shape
+    keep = torch.ones(R, P) if pad is None else (pad == 0).float()
+    return (dy.float()[:, None, :] * (keep * inv[:, None])[:, :, None]).to(BF)
+
+
 def gather_rows(src, ids):
     ok = (ids >= 0) & (ids < src.shape[0])
     out = src[ids.clamp(0, src.shape[0] - 1)].clone()
