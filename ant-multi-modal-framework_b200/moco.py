@@ -121,8 +121,9 @@ class B200MocoUtils(nn.Module):
             end = min(ptr + keys.shape[0], K)
             start = end - keys.shape[0]
             queue[:, start:end] = keys.T.to(queue.dtype)
-            if name in self._shadow:
-                self._shadow[name][:, start:end] = keys.T.to(BF16)
+            # the bf16 image may be held by a pending backward (the reference clones the queue per step, univl_video_ret.py:286,299):
+            # never write into it — drop it, the next loss call re-casts the updated queue
+            self._shadow.pop(name, None)
             ptr_buf[0] = end % K
 
         if self.img_encoder_q is not None and vis_keys is not None:

@@ -82,3 +82,68 @@ def test_world2_gloo(tmp_path):
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+WORKER_STAGE2 = textwrap.dedent(
+    """
+    import os, sys
+    sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import b200mm
+    from oracle import restated
+    from tests import emulated_ops
+    from tests.test_cross_host_cpu import build_scorer, rel_l2
+    BF = torch.bfloat16
+    fx = torch.load(os.path.join(%r, "tests", "golden", "stage2.pt"), weights_only=False)
+    heads = fx["config"]["heads"]
+    sc = build_scorer(fx).to(BF).train()
+    # identical global data on every rank; each rank owns 3 texts and 3 videos
+    g = torch.Generator().manual_seed(5)
+    b, St, Sv, H = 3, 6, 3, 64
+    seq_all = torch.randn(b * world, St, H, generator=g).to(BF).float()
+    vis_all = torch.randn(b * world, Sv, H, generator=g).to(BF).float()
+    am_all = torch.ones(b * world, St, dtype=torch.long); am_all[1, 4:] = 0; am_all[4, 3:] = 0
+    vm_all = torch.ones(b * world, Sv, dtype=torch.long); vm_all[5, 2:] = 0
+    l1 = torch.randn(b * world, b * world, generator=g) + 2.0 * torch.eye(b * world)
+    R = torch.randn(world, b, b, generator=g)
+    sl = slice(rank * b, (rank + 1) * b)
+    seq = seq_all[sl].clone().requires_grad_()
+    vis = vis_all[sl].clone().requires_grad_()
+    with emulated_ops.patched():
+        l2 = sc.cross_similarity_hard_mining((vis, vm_all[sl], None, 1, None), (seq, am_all[sl], None, b, None), l1.clone(), "top_k")
+        (l2 * R[rank]).sum().backward()
+    # oracle: BOTH ranks' computations in one process on the concatenated data
+    sd = {k: v.to(BF).float().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    o_seq, o_vis = seq_all.clone().requires_grad_(), vis_all.clone().requires_grad_()
+    total, mine = 0.0, None
+    for r in range(world):
+        chosen = restated.hard_mining_indices(l1, r * b, b, "top_k")
+        assert chosen.min() >= 0 and chosen.max() < b * world and torch.equal(torch.diagonal(chosen), torch.arange(b) + r * b)
+        o_l2 = restated.cross_similarity_hard_mining(sd, o_seq[r * b:(r + 1) * b], am_all[r * b:(r + 1) * b], o_vis, vm_all, chosen, heads)
+        total = total + (o_l2 * R[r]).sum()
+        if r == rank:
+            mine = o_l2.detach()
+    total.backward()
+    assert rel_l2(l2, mine) < 2e-2, rel_l2(l2, mine)
+    # local text gradient = this rank's term only; local video gradient = the sum over ALL ranks' terms (reduce-scatter of gather_tensor)
+    assert rel_l2(seq.grad, o_seq.grad[sl]) < 8e-2, rel_l2(seq.grad, o_seq.grad[sl])
+    assert rel_l2(vis.grad, o_vis.grad[sl]) < 8e-2, rel_l2(vis.grad, o_vis.grad[sl])
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok2_{rank}"), "w").write("ok")
+    """
+)
+
+
+def test_world2_gloo_stage2_hard_mining(tmp_path):
+    """Stage-2 hard-negative mining across ranks: local texts scored against videos GATHERED from every rank (global indices from the
+    level-1 matrix, beg_idx = rank * bsz), video-token gradients returned home by the reduce-scatter — vs the single-process oracle."""
+    script = tmp_path / "worker_stage2.py"
+    script.write_text(WORKER_STAGE2 % (ROOT, ROOT))
+    port = 29900 + (os.getpid() % 90)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok2_0").exists() and (tmp_path / "ok2_1").exists()
