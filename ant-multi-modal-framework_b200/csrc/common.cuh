@@ -80,21 +80,26 @@ __device__ __forceinline__ float dact_quickgelu(float x) {
 // Phi(x) = 0.5*(1+erf(x/sqrt2)) through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution):
 //   erf(z) = 1 - (a1 t + ... + a5 t^5) e^{-z^2},  t = 1/(1 + p z),  z = |x|/sqrt2  ->  e^{-z^2} = e^{-x^2/2} is also the Gaussian pdf term
 // of the derivative, so gelu and gelu' cost one ex2, one rcp and a short FMA chain instead of libm's erff.
+// gauss_half_tail returns h = 0.5*(1 - erf(|x|/sqrt2)) = 1 - Phi(|x|) (coefficients pre-halved) and expo = exp(-x^2/2):
+// 11 issue slots + 2 MUFU.  gelu(x) = x*Phi(x) = max(x,0) - |x|*h needs no sign select (2 more slots).
+__device__ __forceinline__ float gauss_half_tail(float x, float& expo) {
+  const float xs = x * 0.84932180028801907f;  // xs^2 = x^2 * 0.5*log2(e)
+  expo = fast_ex2(-xs * xs);                  // exp(-x^2/2)
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
+  float poly = fmaf(0.5f * 1.061405429f, t, -0.5f * 1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, -0.5f * 0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  return poly * t * expo;
+}
 __device__ __forceinline__ void gauss_cdf_pdf(float x, float& cdf, float& expo) {
-  const float ax = fabsf(x);
-  expo = fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2/2)
-  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float half_tail = 0.5f * poly * t * expo;  // 0.5*(1 - erf(|x|/sqrt2))
-  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+  const float h = gauss_half_tail(x, expo);
+  cdf = 0.5f + copysignf(0.5f - h, x);  // x >= 0 ? 1 - h : h
 }
 __device__ __forceinline__ float act_gelu_erf(float x) {
-  float cdf, expo;
-  gauss_cdf_pdf(x, cdf, expo);
-  return x * cdf;
+  float expo;
+  const float h = gauss_half_tail(x, expo);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float dact_gelu_erf(float x) {
   float cdf, expo;

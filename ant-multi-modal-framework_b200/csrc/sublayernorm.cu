@@ -78,15 +78,34 @@ __global__ void __launch_bounds__(THREADS, MINB) act_ln_fwd_kernel(const __nv_bf
                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int32_t W,
                                                              float eps) {
   __shared__ float red_a[THREADS / 32], red_b[THREADS / 32];
+  // affine parameters as fp32 in shared memory (2 x 4 B x row width <= 32 KB): the output pass reads them with LDS.128 instead of
+  // unpacking bf16 registers for every row (2 of ~33 issue slots per element in the first version, cuobjdump -sass)
+  // Only with an activation: there the kernel is issue-bound and the saved slots pay (0.59 -> 0.42 ms at 100 864 x 4096); without one it
+  // is HBM-bound and the 32 KB of smem would cost occupancy (0.32 -> 0.35 ms), so the bf16 registers stay (profiles/r01g_subln_sweep.log).
+  constexpr bool kSmemWB = ACT != B200MM_ACT_NONE && VPT * THREADS * 8 * 8 <= 32768;
+  __shared__ __align__(16) float w_s[kSmemWB ? VPT * THREADS * 8 : 4], b_s[kSmemWB ? VPT * THREADS * 8 : 4];
   const float inv_w = 1.f / static_cast<float>(W);
-  uint4 wq[VPT], bq[VPT];
+  uint4 wq[kSmemWB ? 1 : VPT], bq[kSmemWB ? 1 : VPT];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int col = (i * THREADS + threadIdx.x) * 8;
-    wq[i] = bq[i] = make_uint4(0, 0, 0, 0);
+    uint4 wv4 = make_uint4(0, 0, 0, 0), bv4 = make_uint4(0, 0, 0, 0);
     if (col < W) {
-      wq[i] = *reinterpret_cast<const uint4*>(w + col);
-      bq[i] = *reinterpret_cast<const uint4*>(b + col);
+      wv4 = *reinterpret_cast<const uint4*>(w + col);
+      bv4 = *reinterpret_cast<const uint4*>(b + col);
+    }
+    if (kSmemWB) {  // each thread stores (and later reads) only its own columns: no barrier needed
+      float wf[8], bf[8];
+      sl_unpack8(wv4, wf);
+      sl_unpack8(bv4, bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        w_s[col + j] = wf[j];
+        b_s[col + j] = bf[j];
+      }
+    } else {
+      wq[i] = wv4;
+      bq[i] = bv4;
     }
   }
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -113,11 +132,12 @@ __global__ void __launch_bounds__(THREADS, MINB) act_ln_fwd_kernel(const __nv_bf
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
-      const bool valid = (i * THREADS + threadIdx.x) * 8 < W;
+      if ((i * THREADS + threadIdx.x) * 8 < W) {  // padding slots hold act(0) = 0 and must not add mean^2
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[i][j] -= mean;
-        if (valid) sq = fmaf(v[i][j], v[i][j], sq);
+        for (int j = 0; j < 8; ++j) {
+          v[i][j] -= mean;
+          sq = fmaf(v[i][j], v[i][j], sq);
+        }
       }
     }
     const float rstd = rsqrtf(block_sum<THREADS>(sq, red_b) * inv_w + eps);
@@ -131,8 +151,15 @@ __global__ void __launch_bounds__(THREADS, MINB) act_ln_fwd_kernel(const __nv_bf
       const int col = (i * THREADS + threadIdx.x) * 8;
       if (col < W) {
         float wv[8], bv[8], o[8];
-        sl_unpack8(wq[i], wv);
-        sl_unpack8(bq[i], bv);
+        if (kSmemWB) {
+          *reinterpret_cast<float4*>(&wv[0]) = *reinterpret_cast<const float4*>(&w_s[col]);
+          *reinterpret_cast<float4*>(&wv[4]) = *reinterpret_cast<const float4*>(&w_s[col + 4]);
+          *reinterpret_cast<float4*>(&bv[0]) = *reinterpret_cast<const float4*>(&b_s[col]);
+          *reinterpret_cast<float4*>(&bv[4]) = *reinterpret_cast<const float4*>(&b_s[col + 4]);
+        } else {
+          sl_unpack8(wq[i], wv);
+          sl_unpack8(bq[i], bv);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, wv[j], bv[j]);
         *reinterpret_cast<uint4*>(yr + col) = sl_pack8(o);
@@ -147,16 +174,22 @@ __global__ void __launch_bounds__(THREADS, MINB) act_ln_bwd_kernel(const __nv_bf
                                                              const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ du,
                                                              float* __restrict__ dw, float* __restrict__ db, int64_t rows, int32_t W) {
   __shared__ float red1[2][THREADS / 32], red2[2][THREADS / 32];
+  __shared__ __align__(16) float w_s[VPT * THREADS * 8];  // fp32 LN weights (<= 32 KB), thread-private columns: no barrier
   const float inv_w = 1.f / static_cast<float>(W);
-  uint4 wq[VPT];
   float dwv[VPT][8], dbv[VPT][8];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int col = (i * THREADS + threadIdx.x) * 8;
-    wq[i] = make_uint4(0, 0, 0, 0);
-    if (col < W) wq[i] = *reinterpret_cast<const uint4*>(w + col);
+    uint4 wv4 = make_uint4(0, 0, 0, 0);
+    if (col < W) wv4 = *reinterpret_cast<const uint4*>(w + col);
+    float wf[8];
+    sl_unpack8(wv4, wf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dwv[i][j] = 0.f; dbv[i][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+      w_s[col + j] = wf[j];
+      dwv[i][j] = 0.f;
+      dbv[i][j] = 0.f;
+    }
   }
   int par = 0;
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x, par ^= 1) {
@@ -179,7 +212,9 @@ __global__ void __launch_bounds__(THREADS, MINB) act_ln_bwd_kernel(const __nv_bf
       float uv[8], dyv[8], wv[8];
       sl_unpack8(uq[i], uv);
       sl_unpack8(dq[i], dyv);
-      sl_unpack8(wq[i], wv);
+      const int col = (i * THREADS + threadIdx.x) * 8;
+      *reinterpret_cast<float4*>(&wv[0]) = *reinterpret_cast<const float4*>(&w_s[col]);
+      *reinterpret_cast<float4*>(&wv[4]) = *reinterpret_cast<const float4*>(&w_s[col + 4]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float g;
@@ -267,7 +302,8 @@ static SubLnCfg subln_cfg(const char* env, int def_threads, int def_per_sm) {
 template <int ACT>
 int sub_ln_fwd(const __nv_bfloat16* u, const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* y, float* mean, float* rstd, int64_t rows,
                int32_t W, float eps, cudaStream_t st) {
-  SubLnCfg c = subln_cfg("B200MM_SUBLN_FWD", W <= 4096 ? 128 : 256, 8);
+  // CTAs per SM: 6 x 32.8 KB of smem is what fits with the fp32 affine copy (8 would run as two uneven waves: 0.50 vs 0.42 ms)
+  SubLnCfg c = subln_cfg("B200MM_SUBLN_FWD", W <= 4096 ? 128 : 256, ACT != B200MM_ACT_NONE && W > 2048 ? 6 : 8);
   if (ceil_div(W, c.threads * 8) > (c.threads == 512 ? 2 : 4)) c.threads = W <= 4096 ? 128 : 256;  // override does not fit this width
   B200MM_REQUIRE(W <= 8192, B200MM_ERR_SHAPE, "act_layernorm_fwd: width %d not supported (max 8192)", W);
   const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(sm_count()) * c.per_sm));

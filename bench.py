@@ -30,7 +30,9 @@ METRIC = "image-text pairs/sec fwd+bwd"
 FLOP_PER_PAIR = {  # algorithmic fwd+bwd FLOPs per pair, SURVEY.md §8d (GEMMs 24*W^2 + attention 4*L*W per token-layer, x3)
     "ViT-L-14": 526.0e9,
     "ViT-B-16": 145.0e9,
-    "ViT-H-14": None,
+    # ViT-H/14 at 224 (width 1280, 32 layers, 257 tokens, head_dim 80) + BERT-large (width 1024, 24 layers) — configs[4]'s towers at the
+    # resolution CONFIGS["ViT-H-14"] ships (cn_model.py:95-113); attention runs on the mma.sync fallback kernels (head_dim 80)
+    "ViT-H-14": 3 * ((24 * 1280**2 + 4 * 257 * 1280) * 32 * 257 + (24 * 1024**2 + 4 * 77 * 1024) * 24 * 77),
     # M2-Encoder (BEiT-3 multiway, 197 image tokens + 52 text tokens through the same 21+3 / 9+3 layers), same counting rule
     "M2-Encoder-1B": 3 * (24 * 1024**2 + 4 * 197 * 1024) * 24 * 197 + 3 * (24 * 1024**2 + 4 * 52 * 1024) * 24 * 52,
     "M2-Encoder-0.4B": 3 * (24 * 768**2 + 4 * 197 * 768) * 12 * 197 + 3 * (24 * 768**2 + 4 * 52 * 768) * 12 * 52,
@@ -328,7 +330,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(pairs_per_s, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (seeded N(0,1) images, random ids with [CLS]/[SEP]/[PAD]; random-init weights, reference init)",
-            "config": {"workload": (f"BASELINE.json configs[{1 if world == 1 else 2}]: CNCLIP {args.model} + BERT-base, fwd + fused contrastive loss + bwd"
+            "config": {"workload": (f"BASELINE.json configs[{1 if world == 1 else 2}]: CNCLIP {args.model} + BERT-{'large' if args.model == 'ViT-H-14' else 'base'}, fwd + fused contrastive loss + bwd"
                                     if args.model in FLOP_PER_PAIR and not args.model.startswith(("M2", "base_vtp")) else
                                     (f"BASELINE.json configs[3] geometry: base_vtp video-text (arch clip) ViT-B/16 x {VTP_FRAMES} frames + BERT-base, level-1 MIL-NCE + "
                                      f"level-2 cross-modal scoring of B x B mined pairs (86-token sequences) + weighted MIL-NCE, fwd + bwd; {B} pairs per GPU")
