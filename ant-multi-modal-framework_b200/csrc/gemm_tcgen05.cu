@@ -692,19 +692,30 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // sub_diag < 0 ADDS e^{diag[m]} instead (MoCo: LSE over the positive logit and the queue negatives, moco_utils.py:71-81).
 // sub_diag implements MIL-NCE's union {video_j·all texts} ∪ {text_j·videos k != j}, where the positive logit would
 // otherwise be counted twice (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197).
+// One WARP per row: lanes stride over the row's tile partials (coalesced), shuffles reduce max and sum; one loss atomic per CTA.
+// (The first version used one thread per row: strided reads and 4 CTAs for 1024 rows — 43 us per call under ncu, more than the
+// LSE GEMM it follows; profiles/r01h_contrast_bench.log.)
 __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ maxA, const float* __restrict__ sumA, int32_t tA,
                                                         const float* __restrict__ maxB, const float* __restrict__ sumB, int32_t tB,
                                                         const float* __restrict__ diag, int32_t sub_diag, float* __restrict__ lse,
                                                         float* __restrict__ loss_sum, int64_t M) {
-  const int64_t m = blockIdx.x * 256ll + threadIdx.x;
+  __shared__ float cta_term[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m = blockIdx.x * 8ll + warp;
   float term = 0.f;
-  if (m < M) {
+  if (m < M) {  // warp-uniform
+    const float* mA = maxA + m * tA;
+    const float* sA = sumA + m * tA;
+    const float* mB = tB > 0 ? maxB + m * tB : nullptr;
+    const float* sB = tB > 0 ? sumB + m * tB : nullptr;
     float mx = -INFINITY;
-    for (int t = 0; t < tA; ++t) mx = fmaxf(mx, maxA[m * tA + t]);
-    for (int t = 0; t < tB; ++t) mx = fmaxf(mx, maxB[m * tB + t]);
+    for (int t = lane; t < tA; t += 32) mx = fmaxf(mx, mA[t]);
+    for (int t = lane; t < tB; t += 32) mx = fmaxf(mx, mB[t]);
+    mx = warp_max(mx);
     float sm = 0.f;
-    for (int t = 0; t < tA; ++t) sm += sumA[m * tA + t] * __expf(maxA[m * tA + t] - mx);
-    for (int t = 0; t < tB; ++t) sm += sumB[m * tB + t] * __expf(maxB[m * tB + t] - mx);
+    for (int t = lane; t < tA; t += 32) sm += sA[t] * __expf(mA[t] - mx);
+    for (int t = lane; t < tB; t += 32) sm += sB[t] * __expf(mB[t] - mx);
+    sm = warp_sum(sm);
     const float d = diag[m];
     if (sub_diag > 0) {
       sm -= __expf(d - mx);
@@ -714,11 +725,17 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
       mx = nm;
     }
     const float l = mx + __logf(sm);
-    lse[m] = l;
+    if (lane == 0) lse[m] = l;
     term = l - d;
   }
-  term = warp_sum(term);
-  if ((threadIdx.x & 31) == 0 && loss_sum != nullptr) atomicAdd(loss_sum, term);
+  if (lane == 0) cta_term[warp] = term;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_sum != nullptr) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += cta_term[i];
+    atomicAdd(loss_sum, s);
+  }
 }
 
 }  // namespace b200mm
@@ -887,7 +904,7 @@ extern "C" int b200mm_contrast_lse_merge(const float* maxA, const float* sumA, i
                                          void* stream) {
   B200MM_REQUIRE(M > 0 && maxA && sumA && diag && lse && tilesA > 0 && (tilesB == 0 || (maxB && sumB)), B200MM_ERR_SHAPE,
                  "contrast_lse_merge: bad arguments");
-  lse_merge_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  lse_merge_kernel<<<static_cast<int>(ceil_div(M, 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       maxA, sumA, tilesA, maxB, sumB, tilesB, diag, sub_diag, lse, loss_sum, M);
   return check_launch("lse_merge_kernel");
 }

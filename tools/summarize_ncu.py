@@ -38,8 +38,14 @@ def launches(path):
 def full(path):
     r = csv.reader(open(path))
     hdr = next(r)
-    next(r)
+    units = next(r)
     col = {h: i for i, h in enumerate(hdr)}
+    to_gb = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "Tbyte": 1e3}
+    to_us = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+    def val(row, i):  # metric value normalised to GB / us where the unit row says bytes / time
+        v = float(row[i].replace(",", ""))
+        return v * to_gb.get(units[i], 1.0) * (to_us.get(units[i], 1.0) if units[i] in to_us else 1.0)
 
     def find(sub):
         for h, i in col.items():
@@ -59,14 +65,14 @@ def full(path):
         vals = []
         for n, i in idx:
             if i == -1:
-                t = float(row[find("gpu__time_duration.sum")].replace(",", ""))
-                b = float(row[find("dram__bytes_read.sum")].replace(",", "")) + float(row[find("dram__bytes_write.sum")].replace(",", ""))
+                t = val(row, find("gpu__time_duration.sum"))
+                b = val(row, find("dram__bytes_read.sum")) + val(row, find("dram__bytes_write.sum"))
                 vals.append(f"{b / t * 1e3:.2f}")  # GB per us = 1e3 TB/s
                 continue
             if i is None or row[i] == "":
                 vals.append("n/a")
                 continue
-            v = float(row[i].replace(",", ""))
+            v = val(row, i)
             vals.append(f"{v / 1e6:.1f}" if n.startswith("warp inst") else f"{v:.3g}" if v < 100 else f"{v:.1f}")
         print(f"| `{name}` | {row[col['Grid Size']]} | " + " | ".join(vals) + " |")
 
