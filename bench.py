@@ -295,6 +295,8 @@ def run_ours(args):
     peak_tf, peak_hbm, peak_src = peaks()
     gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
+    dominant = dominant_launch(prof, peak_tf) if rank == 0 else None
+
     if args.profile and rank == 0:
         write_profile(args, prof, step, image_d, text_d, B)
 
@@ -347,7 +349,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all tcgen05 GEMM launches of the timed region)",
                          "achieved": round(gemm_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(gemm_tf / peak_tf, 4),
-                         "peak_source": peak_src, "launches": len(prof), "share_of_step": round(gemm_ms / ms_total, 4), "traffic": None,
+                         "peak_source": peak_src, "launches": len(prof), "share_of_step": round(gemm_ms / ms_total, 4),
+                         "traffic": dominant.get("traffic") if dominant else None, "dominant_launch": dominant,
                          "whole_step_frac": round(pairs_per_s / world * fpp / 1e12 / peak_tf, 4) if fpp else None},
         }
         if world == 1 and not args.no_cpu_baseline and args.model in FLOP_PER_PAIR and not args.model.startswith("M2"):  # the oracle port of the headline path
@@ -357,6 +360,38 @@ def run_ours(args):
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out), flush=True)
+
+
+def dominant_launch(gemm_prof, peak_tf):
+    """The GEMM shape/epilogue that takes the most time in the timed region: its own TFLOP/s, algorithmic bytes per launch, and the DRAM
+    traffic ncu measured for one launch of the SAME kernel instantiation at the SAME shape (profiles/ncu_traffic_latest.json, produced from
+    the committed `ncu --set full` capture of tools/prof_kernels.py) — null when that capture does not cover this shape."""
+    from collections import defaultdict
+
+    groups = defaultdict(lambda: [0, 0.0, 0.0])
+    for flops, a, b, splits, tag in gemm_prof:
+        g = groups[tag + (splits,)]
+        g[0] += 1
+        g[1] += a.elapsed_time(b)
+        g[2] += flops
+    if not groups:
+        return None
+    tag, (n, ms, fl) = max(groups.items(), key=lambda kv: kv[1][1])
+    M, N, K, a_mn, b_mn, bias, act, aux, dact, res, f32, splits = tag
+    tf = fl / (ms * 1e-3) / 1e12
+    alg = 2 * (M * K + N * K) + (4 if f32 else 2) * M * N * (1 + aux) + 2 * M * N * (dact + res) + 2 * N * bias
+    flavor = (bias) | (aux << 1) | (res << 2) | (dact << 3) | (f32 << 4) | (act << 6)
+    name = f"gemm_tcgen05_kernel<{a_mn}, {b_mn}, 0, 2, {flavor}>"
+    out = {"kernel": name, "shape_MNK": [M, N, K], "launches": n, "avg_ms": round(ms / n, 4), "achieved": round(tf, 1), "frac": round(tf / peak_tf, 4),
+           "algorithmic_bytes": alg, "traffic": None}
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_latest.json")
+    if os.path.isfile(path) and splits == 1:
+        d = json.load(open(path))
+        k = d.get("kernels", {}).get(name)
+        if k and d.get("shapes", {}).get(name) == [M, N, K]:
+            out["traffic"] = k["dram_bytes"]
+            out["traffic_source"] = d.get("source")
+    return out
 
 
 def write_profile(args, gemm_prof, step, image_d, text_d, B):

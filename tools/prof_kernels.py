@@ -1,4 +1,6 @@
-"""One launch of each hot kernel at (a slice of) the ViT-L/14 bench shapes — the target of the per-kernel ncu captures."""
+"""One launch of each hot kernel at the ViT-L/14 bench shapes — the target of the per-kernel ncu captures. PROF_ROWS = 65 792 (256 images,
+default: the `--set full` capture replays every kernel ~40 times) or 263 168 (1024 images = the bench's per-launch shapes, used with the
+two-metric DRAM-traffic capture that `tools/summarize_ncu.py traffic` turns into profiles/ncu_traffic_latest.json for bench.py)."""
 import os
 import sys
 
@@ -9,7 +11,8 @@ from b200mm import ops
 
 torch.manual_seed(0)
 BF = torch.bfloat16
-T, W = 65792, 1024  # 256 images x 257 tokens
+T, W = int(os.environ.get("PROF_ROWS", 65792)), 1024  # 1024 images x 257 tokens = the bench's per-launch shapes (configs[1])
+NB = T // 257
 x = torch.randn(T, W, device="cuda").to(BF)
 dy = torch.randn(T, W, device="cuda").to(BF)
 w = torch.ones(W, device="cuda", dtype=BF)
@@ -32,9 +35,22 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     dwp = ops.gemm(dy, g, a_mn=True, b_mn=True)
     # attention fwd / bwd, 256 x 16 heads x 257 tokens
     qkv = torch.randn(T, 3 * W, device="cuda").to(BF)
-    o, lse = ops.attention_fwd(qkv, 256, 257, 16, 64)
-    dqkv = ops.attention_bwd(qkv, o, dy, lse, 256, 257, 16, 64)
+    o, lse = ops.attention_fwd(qkv, NB, 257, 16, 64)
+    dqkv = ops.attention_bwd(qkv, o, dy, lse, NB, 257, 16, 64)
     ops.rowsum_periodic(du, torch.zeros(4 * W, device="cuda"))
     ops.act_fwd(u, ops.ACT_QUICKGELU)
+    # M2-Encoder sub-LayerNorm over the 4W-wide FFN hidden: gelu + LN forward, LN' * gelu' backward
+    w4 = torch.ones(4 * W, device="cuda", dtype=BF)
+    b4 = torch.zeros(4 * W, device="cuda", dtype=BF)
+    gn, m4, r4 = ops.act_layernorm_fwd(u, ops.ACT_GELU_ERF, w4, b4, 1e-5)
+    ops.act_layernorm_bwd(du, u, ops.ACT_GELU_ERF, m4, r4, w4, torch.zeros(4 * W, device="cuda"), torch.zeros(4 * W, device="cuda"))
+    # stage-2 pair gather: 1024 pairs x 79 tokens x 768 from a 64 x 79-row table
+    tab = torch.randn(64 * 79, 768, device="cuda").to(BF)
+    ids = torch.randint(0, 64 * 79, (1024 * 79,), device="cuda")
+    ops.gather_rows(tab, ids)
+    # contrastive LSE partials + merge at the configs[2] per-rank size
+    ia = torch.nn.functional.normalize(torch.randn(8192, 768, device="cuda"), dim=-1).to(BF)
+    pm = ops.contrast_lse_partials(ia[:1024].contiguous(), ia, 14.3, 0)
+    ops.contrast_lse_merge(pm[:2], None, pm[2], False, torch.zeros(1, device="cuda"))
 torch.cuda.synchronize()
 print("done")

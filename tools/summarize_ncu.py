@@ -77,5 +77,45 @@ def full(path):
         print(f"| `{name}` | {row[col['Grid Size']]} | " + " | ".join(vals) + " |")
 
 
+def traffic(path):
+    """JSON from the long-format CSV of `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv`:
+    first captured launch of each kernel -> measured time and DRAM bytes."""
+    import json
+
+    lines = [l for l in open(path) if not l.startswith("==")]
+    to_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    to_us = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
+    per_id, order = {}, []
+    for row in csv.DictReader(lines):
+        name = re.sub(r"\(.*", "", re.sub(r"^void ", "", row["Kernel Name"])).replace("b200mm::", "")
+        key = row["ID"]
+        if key not in per_id:
+            per_id[key] = {"name": name, "grid": row["Grid Size"]}
+            order.append(key)
+        v = float(row["Metric Value"].replace(",", ""))
+        m, u = row["Metric Name"], row["Metric Unit"]
+        if m == "gpu__time_duration.sum":
+            per_id[key]["time_us"] = round(v * to_us.get(u, 1.0), 2)
+        elif m == "dram__bytes_read.sum":
+            per_id[key]["dram_read_bytes"] = int(v * to_b.get(u, 1.0))
+        elif m == "dram__bytes_write.sum":
+            per_id[key]["dram_write_bytes"] = int(v * to_b.get(u, 1.0))
+    out = {}
+    for key in order:
+        d = per_id[key]
+        if d["name"] in out or "dram_read_bytes" not in d:
+            continue
+        d["dram_bytes"] = d["dram_read_bytes"] + d.get("dram_write_bytes", 0)
+        out[d.pop("name")] = d
+    T = int(sys.argv[3]) if len(sys.argv) > 3 else 263168
+    # [M, N, K] of the GEMM launches tools/prof_kernels.py makes, by kernel instantiation (flavor = epilogue bits, gemm_tcgen05.cu flavor_bits)
+    shapes = {"gemm_tcgen05_kernel<0, 0, 0, 2, 67>": [T, 4096, 1024],   # c_fc forward: bias + QuickGELU + pre-activation copy
+              "gemm_tcgen05_kernel<0, 1, 0, 2, 72>": [T, 4096, 1024],   # dgrad through the activation (x act'(u))
+              "gemm_tcgen05_kernel<0, 0, 0, 2, 5>": [T, 1024, 4096]}    # c_proj forward: bias + residual
+    print(json.dumps({"source": path, "how": f"PROF_ROWS={T} ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum "
+                      "--clock-control none python tools/prof_kernels.py 1 (one launch per kernel)",
+                      "shapes": {k: v for k, v in shapes.items() if k in out}, "kernels": out}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
