@@ -243,3 +243,77 @@ class B200VideoTextRetrieval(nn.Module):
     def forward(self, img_input, caption_input, ocr_input=None, region_input=None, caption_output=None, sample_list=None):
         cap_input, vis_input, _, _ = self.module.get_l2_input(img_input, caption_input)
         return self.forward_stage(cap_input + (caption_input,), vis_input + (img_input,), True)
+
+
+# ======================================================================================================================
+# Model plug-in: antmmf `registry.register_model` API (antmmf/common/registry.py:415-440, models/build.py:9-25)
+# ======================================================================================================================
+try:  # pragma: no cover - only with a full AntMMF installation
+    from antmmf.models.base_model import BaseModel as _BaseModel  # type: ignore
+except Exception:  # noqa: BLE001
+    _BaseModel = None
+
+
+class B200Univl(_BaseModel if _BaseModel is not None else nn.Module):
+    """`Univl` (prj/base_vtp/roi_univl/univl/model/univl_model.py:16-125) for training_head_type 'video_text_retrieval': same
+    build() / group_inputs() / forward(sample_list) -> {"losses": {...}, "l1_simi", "l2_simi"} / get_optimizer_parameters(config).
+    Registered as "b200_univl"; `install_as_univl()` also claims the key "univl", which the unmodified trainer requires
+    (base_trainer.py:552-556 reads config.model_attributes.univl on every iteration)."""
+
+    def __init__(self, config):
+        if _BaseModel is not None:
+            super().__init__(config)
+        else:
+            super().__init__()
+            self.config = config
+
+    def build(self):
+        head = _get(self.config, "training_head_type", "video_text_retrieval")
+        if head != "video_text_retrieval":
+            raise NotImplementedError(f"b200mm Univl: training_head_type {head!r}; only 'video_text_retrieval' is on the hot path")
+        self.model = B200VideoTextRetrieval(self.config)
+        self.get_l2_input = self.model.module.get_l2_input  # modality features for retrieval evaluation (univl_model.py:30-31)
+
+    @staticmethod
+    def group_inputs(sample_list):
+        groups = {"ocr": None, "caption": None, "region": None, "image": None, "generation": None}
+        for sample_key in sample_list.keys():
+            for input_key in groups:
+                if sample_key.startswith(input_key):
+                    if groups[input_key] is None:
+                        groups[input_key] = {}
+                    groups[input_key][sample_key] = sample_list[sample_key]
+        return groups
+
+    def forward(self, sample_list, *args, **kwargs):
+        g = self.group_inputs(sample_list)
+        out = self.model(g["image"], g["caption"], g["ocr"], g["region"], caption_output=g["generation"], sample_list=sample_list)
+        return {"logits": out} if isinstance(out, torch.Tensor) else out
+
+    def get_optimizer_parameters(self, config):
+        """UnivlForVideoTextRetrieval.get_optimizer_parameters (univl_video_ret.py:478-537): pretrained tower parameters at
+        lr * encoder_lr_decay, new modules at lr; biases / LayerNorm affine without weight decay."""
+        lr = config.optimizer_attributes.params.lr
+        weight_decay = config.optimizer_attributes.params.weight_decay
+        decay = _get(self.config, "encoder_lr_decay", 0.01)
+        no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+        pretrain_prefix = ["text_encoder.embeddings.", "text_encoder.encoder.", "text_encoder.pooler.", "img_embeddings.", "img_encoder."]
+        groups = {(d, c): [] for d in (True, False) for c in (True, False)}
+        for n, p in self.model.named_parameters():
+            groups[(not any(nd in n for nd in no_decay), any(pre in n for pre in pretrain_prefix))].append(p)
+        return [
+            {"params": groups[(True, True)], "weight_decay": weight_decay, "lr": lr * decay},
+            {"params": groups[(True, False)], "weight_decay": weight_decay},
+            {"params": groups[(False, True)], "weight_decay": 0.0, "lr": lr * decay},
+            {"params": groups[(False, False)], "weight_decay": 0.0},
+        ]
+
+
+from .registry import registry as _registry  # noqa: E402
+
+_registry.register_model("b200_univl")(B200Univl)
+
+
+def install_as_univl():
+    """Claim the model key "univl" (the only key the unmodified trainer can run, see the class docstring)."""
+    _registry.register_model("univl")(B200Univl)

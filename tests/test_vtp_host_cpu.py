@@ -92,3 +92,42 @@ def test_vtp_stage1_only_and_unsupported_arch():
     assert not hasattr(m, "similarity_dense") and m.module.with_cross_encoder is False
     with pytest.raises(NotImplementedError):
         vtp.B200VideoTextRetrieval(dict(cfg, arch_type="univl"))
+
+
+def test_univl_model_plugin_interface(monkeypatch):
+    """The registered model (antmmf registry.register_model API): build(), forward(sample_list) with the reference's key-prefix grouping
+    (univl_model.py:35-50), get_optimizer_parameters with the reference's four groups (univl_video_ret.py:478-537)."""
+    import types
+
+    from b200mm import vtp
+    from b200mm.registry import registry
+
+    assert registry.get_model_class("b200_univl") is vtp.B200Univl
+    vtp.install_as_univl()
+    assert registry.get_model_class("univl") is vtp.B200Univl
+    cfg = dict(vtp_common.make_config(hard=True), training_head_type="video_text_retrieval", encoder_lr_decay=0.01)
+    torch.manual_seed(0)
+    m = registry.get_model_class("univl")(cfg)
+    m.build()
+    vtp_common.randomize(m.model)
+    m = m.to(BF).train()
+    img_input, caption = vtp_common.make_batch()
+    sample_list = {**img_input, **caption}
+    monkeypatch.setattr(vtp, "mil_nce_loss", lambda v, t, group, n_clips=1: restated.mil_nce_clips(restated.l1_simi_matrix(t.float(), v.float(), n_clips)))
+    with emulated_ops.patched():
+        out = m(sample_list)
+        direct = m.model(img_input, caption)
+    assert set(out["losses"]) == {"level1_similarity_loss", "level2_similarity_loss"}
+    assert torch.equal(out["l2_simi"], direct["l2_simi"])
+    opt_cfg = types.SimpleNamespace(optimizer_attributes=types.SimpleNamespace(params=types.SimpleNamespace(lr=1e-4, weight_decay=0.05)))
+    groups = m.get_optimizer_parameters(opt_cfg)
+    assert len(groups) == 4 and groups[0]["lr"] == groups[2]["lr"] == 1e-4 * 0.01 and "lr" not in groups[1] and groups[2]["weight_decay"] == 0.0
+    ids = [id(p) for g in groups for p in g["params"]]
+    assert len(ids) == len(set(ids)) == len(list(m.model.parameters()))
+    named = dict(m.model.named_parameters())
+    assert any(p is named["similarity_dense.0.weight"] for p in groups[1]["params"])
+    assert any(p is named["similarity_dense.0.bias"] for p in groups[3]["params"])
+    assert any(p is named["module.img_encoder.visual.conv1.weight"] for p in groups[0]["params"])
+    with pytest.raises(NotImplementedError):
+        bad = vtp.B200Univl(dict(cfg, training_head_type="pretraining"))
+        bad.build()
