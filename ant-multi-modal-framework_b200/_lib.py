@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200mm_relu_bwd": (c_int32, [_P, _P, _P, c_int64, _P]),
     "b200mm_mil_nce_matrix_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int32, _P]),
     "b200mm_mil_nce_matrix_bwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int32, _P]),
+    "b200mm_xpos_apply": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, _P]),
     "b200mm_act_fwd": (c_int32, [_P, _P, c_int64, c_int32, _P]),
     "b200mm_rowsum_periodic": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P]),
     "b200mm_scatter_add_rows": (c_int32, [_P, _I64P, _P, c_int64, c_int32, c_int64, c_int64, _P]),

@@ -329,12 +329,14 @@ class RowNormFn(Function):
 # M²-Encoder (BEiT-3 multiway) encoder layer: pre-LN + sub-LN — prj/M2_Encoder/vlmo/torchscale/architecture/encoder.py:113-168,
 # attention component/multihead_attention.py:66-154, FFN component/feedforward_network.py:117-128
 # ======================================================================================================================
-def _m2_layer_forward(x, p, key_bias, B, L, H, eps):
+def _m2_layer_forward(x, p, key_bias, B, L, H, eps, xpos=None):
     (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b) = p
     W = x.shape[1]
     h1, _, mean1, rstd1 = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
     qkv = ops.gemm(h1, qkv_w, bias=qkv_b)
     del h1
+    if xpos is not None:  # optional rotary embedding (XPOS, multihead_attention.py:112-118), in place on the q / k sections
+        ops.xpos_apply(qkv, xpos, B, L, H, W // H)
     # the reference scales q by hd^-0.5 before q·k^T (multihead_attention.py:95); the kernel applies the same factor to the scores
     a, lse = ops.attention_fwd(qkv, B, L, H, W // H, key_bias=key_bias)
     a_n, _, mean_i, rstd_i = ops.layernorm_fwd(a, iln_w, iln_b, eps)  # inner_attn_ln on the merged heads (:148-149)
@@ -353,13 +355,14 @@ class M2EncoderLayerFn(Function):
 
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, q_w, q_b, k_w, k_b, v_w, v_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b,
-                fc2_w, fc2_b, key_bias, B, L, H, eps, checkpoint, keep_act):
+                fc2_w, fc2_b, key_bias, B, L, H, eps, checkpoint, keep_act, xpos=None):
         qkv_w = torch.cat([q_w, k_w, v_w], dim=0)
         qkv_b = torch.cat([q_b, k_b, v_b], dim=0)
         p = (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b)
-        y, saved, g_n = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+        y, saved, g_n = _m2_layer_forward(x, p, key_bias, B, L, H, eps, xpos)
         keep_act = bool(keep_act) and not checkpoint
         ctx.meta = (B, L, H, eps, checkpoint, key_bias is not None, keep_act)
+        ctx.xpos = xpos  # constant f32 tables (no gradient), kept by reference
         kb = (key_bias,) if key_bias is not None else ()
         if checkpoint:
             ctx.save_for_backward(x, *p, *kb)
@@ -379,7 +382,7 @@ class M2EncoderLayerFn(Function):
         (ln1_w, ln1_b, qkv_w, qkv_b, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b) = p
         g_n = None
         if checkpoint:
-            _, rest, g_n = _m2_layer_forward(x, p, key_bias, B, L, H, eps)
+            _, rest, g_n = _m2_layer_forward(x, p, key_bias, B, L, H, eps, ctx.xpos)
         elif keep_act:
             rest, g_n = rest[:-1], rest[-1]
         mean1, rstd1, qkv, a, lse, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f = rest
@@ -415,6 +418,8 @@ class M2EncoderLayerFn(Function):
         del da_n
         dqkv = ops.attention_bwd(qkv, a, da, lse, B, L, H, W // H, key_bias=key_bias)
         del da
+        if ctx.xpos is not None:  # gradient w.r.t. the rotated q / k -> w.r.t. the projection output (transposed rotation)
+            ops.xpos_apply(dqkv, ctx.xpos, B, L, H, W // H, backward=True)
         h1, _, _, _ = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
         d_qkv_w = _wgrad(dqkv, h1)
         del h1
@@ -426,7 +431,7 @@ class M2EncoderLayerFn(Function):
         dq_w, dk_w, dv_w = d_qkv_w[:W], d_qkv_w[W: 2 * W], d_qkv_w[2 * W:]
         dq_b, dk_b, dv_b = d_qkv_b[:W], d_qkv_b[W: 2 * W], d_qkv_b[2 * W:]
         return (dx, d_ln1_w, d_ln1_b, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_iln_w, d_iln_b, d_o_w, d_o_b, d_ln2_w, d_ln2_b, d_fc1_w, d_fc1_b,
-                d_fln_w, d_fln_b, d_fc2_w, d_fc2_b, None, None, None, None, None, None, None)
+                d_fln_w, d_fln_b, d_fc2_w, d_fc2_b, None, None, None, None, None, None, None, None)
 
 
 class LayerNormFn(Function):

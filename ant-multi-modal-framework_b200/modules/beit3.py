@@ -13,7 +13,8 @@ Mirrors, with the same attribute / state-dict names, so that reference checkpoin
 The nn.Linear / nn.LayerNorm / nn.Embedding objects below are PARAMETER CONTAINERS with the reference names; their own
 forward is never called — every layer runs through b200mm.functional (hand-written CUDA behind the C-ABI).
 Supported configuration = what the shipped configs use (configs/Encoder_0.4B.json, Encoder_1B.json): pre-LN + sub-LN,
-no deepnorm / MoE / XPOS / relative position bias, dropout and drop-path 0, head_dim 64. A multiway split inside one
+no deepnorm / MoE / relative position bias, dropout and drop-path 0, head_dim 64; XPOS (args.xpos_rel_pos, off in the shipped configs) is
+supported as an in-place rotary step on the fused QKV output. A multiway split inside one
 sequence (fused vision+language input, split_position > 0) is not on the ITC path and raises.
 """
 import math
@@ -31,6 +32,21 @@ MASK_BIAS = -30000.0  # additive key bias standing for masked_fill(-inf) (multih
 
 def _bf16(t):
     return t if t.dtype == BF16 else t.to(BF16)
+
+
+def xpos_tables(L, head_dim, scale_base=512, device="cpu"):
+    """(q_cos, q_sin, k_cos, k_sin), f32 [L, head_dim/2]: the tables XPOS.forward builds for offset 0 — q with `scale`, k with 1/scale
+    (downscale=True) — written with the reference's own expressions (xpos_relative_position.py:9-13, :41-61) so the values are identical."""
+    base = (torch.arange(0, head_dim, 2) + 0.4 * head_dim) / (1.4 * head_dim)
+    min_pos = -(L + 0) // 2
+    max_pos = L + 0 + min_pos
+    scale = base ** torch.arange(min_pos, max_pos, 1).to(base).div(scale_base)[:, None]
+    seq_len, dim = scale.shape
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, dim) / dim))
+    sinusoid = torch.einsum("i , j -> i j", torch.arange(0, seq_len, dtype=torch.float), inv_freq).to(scale)
+    sin, cos = torch.sin(sinusoid), torch.cos(sinusoid)
+    out = (cos * scale, sin * scale, cos * (1 / scale), sin * (1 / scale))
+    return tuple(t.float().contiguous().to(device) for t in out)
 
 
 class MultiwayNetwork(nn.Module):
@@ -60,9 +76,11 @@ class FeedForwardNetwork(nn.Module):
 
 
 class MultiheadAttention(nn.Module):
-    def __init__(self, embed_dim, num_heads, eps):
+    def __init__(self, embed_dim, num_heads, eps, xpos_rel_pos=False, xpos_scale_base=512):
         super().__init__()
         self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.xpos_rel_pos, self.xpos_scale_base = xpos_rel_pos, xpos_scale_base
+        self._xpos_cache = {}
         self.head_dim = embed_dim // num_heads
         self.scaling = self.head_dim ** -0.5
         lin = lambda: nn.Linear(embed_dim, embed_dim, bias=True)  # noqa: E731
@@ -72,14 +90,23 @@ class MultiheadAttention(nn.Module):
         self.out_proj = MultiwayNetwork(lin)
         self.inner_attn_ln = MultiwayNetwork(lambda: nn.LayerNorm(embed_dim, eps=eps))
 
+    def xpos(self, L, device):
+        """XPOS tables for sequences of length L (None when args.xpos_rel_pos is off, the shipped default)."""
+        if not self.xpos_rel_pos:
+            return None
+        key = (L, str(device))
+        if key not in self._xpos_cache:
+            self._xpos_cache[key] = xpos_tables(L, self.head_dim, self.xpos_scale_base, device)
+        return self._xpos_cache[key]
+
 
 class EncoderLayer(nn.Module):
     """architecture/encoder.py:29-168 with encoder_normalize_before=True, subln=True, alpha=1."""
 
-    def __init__(self, embed_dim, num_heads, ffn_dim, eps):
+    def __init__(self, embed_dim, num_heads, ffn_dim, eps, xpos_rel_pos=False, xpos_scale_base=512):
         super().__init__()
         self.embed_dim, self.eps = embed_dim, eps
-        self.self_attn = MultiheadAttention(embed_dim, num_heads, eps)
+        self.self_attn = MultiheadAttention(embed_dim, num_heads, eps, xpos_rel_pos, xpos_scale_base)
         self.self_attn_layer_norm = MultiwayNetwork(lambda: nn.LayerNorm(embed_dim, eps=eps))
         self.ffn = MultiwayNetwork(lambda: FeedForwardNetwork(embed_dim, ffn_dim, eps))
         self.final_layer_norm = MultiwayNetwork(lambda: nn.LayerNorm(embed_dim, eps=eps))
@@ -96,7 +123,7 @@ class EncoderLayer(nn.Module):
 
     def forward_tokens(self, x2d, key_bias, B, L, split_position):
         return Fn.M2EncoderLayerFn.apply(x2d, *self.layer_params(split_position), key_bias, B, L, self.self_attn.num_heads, self.eps,
-                                         self.checkpoint, self.keep_act)
+                                         self.checkpoint, self.keep_act, self.self_attn.xpos(L, x2d.device))
 
 
 class PositionalEmbedding(nn.Embedding):
@@ -113,11 +140,12 @@ class Encoder(nn.Module):
     """architecture/encoder.py:171-482 for the configuration named in the module docstring. Works on token matrices
     [B*L, W] (batch-first rows); `forward` keeps the reference's keyword interface and returns the same dict keys."""
 
-    def __init__(self, embed_dim=768, attention_heads=12, ffn_dim=3072, layers=12, eps=1e-5, embed_positions=None):
+    def __init__(self, embed_dim=768, attention_heads=12, ffn_dim=3072, layers=12, eps=1e-5, embed_positions=None, xpos_rel_pos=False,
+                 xpos_scale_base=512):
         super().__init__()
         self.embed_dim, self.eps = embed_dim, eps
         self.embed_positions = embed_positions
-        self.layers = nn.ModuleList([EncoderLayer(embed_dim, attention_heads, ffn_dim, eps) for _ in range(layers)])
+        self.layers = nn.ModuleList([EncoderLayer(embed_dim, attention_heads, ffn_dim, eps, xpos_rel_pos, xpos_scale_base) for _ in range(layers)])
         self.num_layers = layers
         self.layer_norm = MultiwayNetwork(lambda: nn.LayerNorm(embed_dim, eps=eps))
         # subln init (encoder.py:262-269): fc1 / fc2 / out_proj / v_proj scaled by sqrt(log(2·layers))
@@ -192,7 +220,8 @@ class BEiT3(nn.Module):
     """model/BEiT3.py:15-96. forward(textual_tokens=…, text_padding_position=…) or forward(visual_tokens=…)."""
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, vocab_size=64010, encoder_embed_dim=768, encoder_attention_heads=12,
-                 encoder_ffn_embed_dim=3072, encoder_layers=12, max_source_positions=1024, layernorm_eps=1e-5):
+                 encoder_ffn_embed_dim=3072, encoder_layers=12, max_source_positions=1024, layernorm_eps=1e-5, xpos_rel_pos=False,
+                 xpos_scale_base=512):
         super().__init__()
         W = encoder_embed_dim
         self.text_embed = nn.Embedding(vocab_size, W)
@@ -200,7 +229,8 @@ class BEiT3(nn.Module):
         self.vision_embed = VisionEmbedding(img_size, patch_size, in_chans, W)
         embed_positions = _MultiwayEmbedding(PositionalEmbedding(self.vision_embed.num_position_embeddings() + 2, W),
                                              PositionalEmbedding(max_source_positions, W))
-        self.encoder = Encoder(W, encoder_attention_heads, encoder_ffn_embed_dim, encoder_layers, layernorm_eps, embed_positions)
+        self.encoder = Encoder(W, encoder_attention_heads, encoder_ffn_embed_dim, encoder_layers, layernorm_eps, embed_positions, xpos_rel_pos,
+                               xpos_scale_base)
 
     def forward_tokens(self, textual_tokens=None, visual_tokens=None, text_padding_position=None):
         """-> ([B*L, W] hidden after the final layer_norm, B, L, drop, key_bias)"""
@@ -259,15 +289,17 @@ class M2Encoder(nn.Module):
     batch dicts; `itc_loss` is the symmetric InfoNCE over both head pairs on the fused similarity / log-softmax kernels."""
 
     def __init__(self, image_size=224, patch_size=16, vocab_size=115244, encoder_embed_dim=768, encoder_attention_heads=12, encoder_layers=9,
-                 beit3_vl_layers=3, out_embed_dim=768, max_text_len=52, mlp_ratio=4, max_source_positions=1024):
+                 beit3_vl_layers=3, out_embed_dim=768, max_text_len=52, mlp_ratio=4, max_source_positions=1024, xpos_rel_pos=False,
+                 xpos_scale_base=512):
         super().__init__()
         W = encoder_embed_dim
         self.img_size, self.num_features, self.out_features, self.max_text_len = image_size, W, out_embed_dim, max_text_len
         self.backbone = BEiT3(image_size, patch_size, 3, vocab_size, W, encoder_attention_heads, int(W * mlp_ratio), encoder_layers,
-                              max_source_positions)
+                              max_source_positions, xpos_rel_pos=xpos_rel_pos, xpos_scale_base=xpos_scale_base)
         self.use_vl = beit3_vl_layers > 0
         if self.use_vl:
-            self.backbone_vl = Encoder(W, encoder_attention_heads, int(W * mlp_ratio), beit3_vl_layers)
+            self.backbone_vl = Encoder(W, encoder_attention_heads, int(W * mlp_ratio), beit3_vl_layers, xpos_rel_pos=xpos_rel_pos,
+                                       xpos_scale_base=xpos_scale_base)
         self.norm = nn.LayerNorm(W, eps=1e-6)  # present in the reference state dict, unused on the ITC path (:176)
         self.pooler = Pooler(W)
         self.itc_text_proj = ITCHead(W, out_embed_dim)

@@ -509,3 +509,18 @@ def mil_nce_matrix_bwd(S, w, lse, gout):
                "b200mm_mil_nce_matrix_bwd")
     _count(1)
     return dS
+
+
+def xpos_apply(qkv, tables, B, L, H, hd, backward=False, q_off=0, k_off=None):
+    """In place: XPOS rotation + scale of the q and k sections of qkv [B*L, ld]; tables = (q_cos, q_sin, k_cos, k_sin), f32 [L, hd/2]."""
+    lib = _lib.load()
+    ld = _row_major_2d(qkv, "qkv")
+    k_off = H * hd if k_off is None else k_off
+    for t in tables:
+        _req(t, "xpos table", torch.float32, 2)
+        if tuple(t.shape) != (L, hd // 2) or not t.is_contiguous():
+            raise _lib.B200mmError(f"b200mm.xpos_apply: tables must be contiguous [L, hd/2] = [{L}, {hd // 2}], got {tuple(t.shape)}")
+    _lib.check(lib.b200mm_xpos_apply(_ptr(qkv), ld, q_off, k_off, _ptr(tables[0]), _ptr(tables[1]), _ptr(tables[2]), _ptr(tables[3]), B * L, L, H, hd,
+                                     int(backward), _stream()), "b200mm_xpos_apply")
+    _count(1)
+    return qkv

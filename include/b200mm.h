@@ -182,6 +182,12 @@ int b200mm_relu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* st
  * bwd: dS [B,B] f32 = (*gout / B) * dLoss/dS with the saved lse. */
 int b200mm_mil_nce_matrix_fwd(const float* S, int64_t ld, const float* w, float* lse, float* loss_sum, int32_t B, void* stream);
 int b200mm_mil_nce_matrix_bwd(const float* S, int64_t ld, const float* w, const float* lse, const float* gout, float* dS, int32_t B, void* stream);
+/* XPOS rotary position embedding (the optional RoPE of the path: prj/M2_Encoder/vlmo/torchscale/component/xpos_relative_position.py:15-62,
+ * multihead_attention.py:112-118), in place on the q and k sections of the fused projection output qkv [T, ld] (T = B*L rows, sections of
+ * H*hd columns at q_off / k_off): pair (2i, 2i+1) of every head is rotated and scaled with the f32 tables [L, hd/2]
+ * q_cos/q_sin = cos/sin(l*inv_freq_i)*scale[l,i], k_cos/k_sin = the same with 1/scale. backward != 0 applies the transposed map. */
+int b200mm_xpos_apply(void* qkv, int64_t ld, int32_t q_off, int32_t k_off, const float* q_cos, const float* q_sin, const float* k_cos,
+                      const float* k_sin, int64_t T, int32_t L, int32_t H, int32_t hd, int32_t backward, void* stream);
 /* y = act(x), bf16, n % 8 == 0 (activation recompute in backward: QuickGELU clip/model.py:222-224, erf-GELU modeling_bert.py:31-37) */
 int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream);
 /* out[(row % period), :] += in[row, :]  (f32 atomics, caller zero-fills): period 1 = bias gradient of nn.Linear,

@@ -153,7 +153,8 @@ def make_retrieval():
     print("retrieval.pt", out["square"]["recall"], out["multi_gt"]["metrics"])
 
 
-def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, patch=8, vocab=256, L=12, B=5, out_dim=32):
+def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, patch=8, vocab=256, L=12, B=5, out_dim=32, xpos=False,
+            max_source_positions=1024):
     """M²-Encoder path with the UNMODIFIED reference classes. VLMo itself is a LightningModule whose constructor loads
     tokenizers/timm (not importable here), so its infer_image / infer_text bodies (vlmo_module.py:323-405) are composed
     here line by line from the same sub-modules and parameter names (backbone, backbone_vl, itc_*_proj, logit_*scale)."""
@@ -166,7 +167,8 @@ def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, pat
     args = m2.EncoderConfig(img_size=img, patch_size=patch, vocab_size=vocab, multiway=True, layernorm_embedding=False,
                             normalize_output=True, no_output_layer=True, drop_path_rate=0, encoder_embed_dim=W,
                             encoder_attention_heads=heads, encoder_layers=layers, encoder_ffn_embed_dim=4 * W,
-                            checkpoint_activations=False, max_text_len=L)
+                            checkpoint_activations=False, max_text_len=L, xpos_rel_pos=xpos, xpos_scale_base=512,
+                            max_source_positions=max_source_positions)
     model = torch.nn.Module()
     model.backbone = m2.BEiT3(args)
     vl_args = copy.copy(args)
@@ -212,7 +214,8 @@ def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, pat
     loss = 0.5 * (F.cross_entropy(lg, labels) + F.cross_entropy(lg.t(), labels)) + 0.5 * (F.cross_entropy(lgv, labels) + F.cross_entropy(lgv.t(), labels))
     loss.backward()
     fx = {
-        "config": dict(W=W, heads=heads, layers=layers, vl_layers=vl_layers, img=img, patch=patch, vocab=vocab, L=L, out_dim=out_dim),
+        "config": dict(W=W, heads=heads, layers=layers, vl_layers=vl_layers, img=img, patch=patch, vocab=vocab, L=L, out_dim=out_dim,
+                       xpos=xpos, max_source_positions=max_source_positions),
         "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
         "image": image, "ids": ids, "masks": masks,
         "image_hidden": vffn.detach(), "text_hidden": lffn.detach(),
@@ -293,6 +296,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--m2-only" in sys.argv:
         make_m2()
+        make_m2("m2_tiny_xpos.pt", layers=1, vl_layers=1, L=11, B=4, xpos=True, max_source_positions=32)
+        sys.exit(0)
+    if "--m2-xpos-only" in sys.argv:
+        make_m2("m2_tiny_xpos.pt", layers=1, vl_layers=1, L=11, B=4, xpos=True, max_source_positions=32)
         sys.exit(0)
     if "--retrieval-only" in sys.argv:
         make_retrieval()
@@ -308,4 +315,5 @@ if __name__ == "__main__":
     make_losses()
     make_retrieval()
     make_m2()
+    make_m2("m2_tiny_xpos.pt", layers=1, vl_layers=1, L=11, B=4, xpos=True, max_source_positions=32)
     make_stage2()

@@ -255,7 +255,26 @@ def to_dtype(sd, dtype):
 # ----------------------------------------------------------------------------------------------------------------
 # M²-Encoder (BEiT-3 multiway transformer)  — prj/M2_Encoder/vlmo  
 # ----------------------------------------------------------------------------------------------------------------
-def m2_attention(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
+def xpos(x, scale_base=512, downscale=False):
+    """XPOS.forward for offset 0 (vlmo/torchscale/component/xpos_relative_position.py:41-61) on x [N, L, hd]: per-position, per-pair scale
+    zeta_i^(pos/scale_base) with zeta_i = (2i + 0.4 hd)/(1.4 hd) and pos in [-(L//2 rounded up), ...), sin/cos of (l * 10000^(-i/(hd/2)))
+    for l = 0..L-1 (:9-13), "rotate every two" pairing (:17-21); k uses 1/scale."""
+    N, L, hd = x.shape
+    base = (torch.arange(0, hd, 2) + 0.4 * hd) / (1.4 * hd)
+    min_pos = -(L // 2) if L % 2 == 0 else -((L + 1) // 2)  # python: -(L) // 2 floors
+    pos = torch.arange(min_pos, min_pos + L).to(base)
+    scale = base[None, :] ** (pos[:, None] / scale_base)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, hd // 2) / (hd // 2)))
+    ang = torch.arange(L, dtype=torch.float)[:, None] * inv_freq[None, :]
+    if downscale:
+        scale = 1 / scale
+    cs = (torch.cos(ang) * scale).repeat_interleave(2, dim=1).to(x)
+    sn = (torch.sin(ang) * scale).repeat_interleave(2, dim=1).to(x)
+    rot = torch.stack((-x[..., 1::2], x[..., ::2]), dim=-1).flatten(-2)
+    return x * cs + rot * sn
+
+
+def m2_attention(sd, pfx, x, heads, way, key_pad=None, eps=1e-5, xpos_scale_base=None):
     """MultiheadAttention.forward, vlmo/torchscale/component/multihead_attention.py:66-154 with the multiway expert
     `way` ("A" vision / "B" language, multiway_network.py:33-45): q scaled by hd^-0.5 BEFORE q·k^T (:95), key padding
     → -inf (:129-135), softmax in fp32 (:141), sub-LN `inner_attn_ln` on the merged heads (:148-149), out_proj (:151)."""
@@ -265,6 +284,9 @@ def m2_attention(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
     q = (lin("q_proj", x) * hd ** -0.5).view(B, L, heads, hd).transpose(1, 2)
     k = lin("k_proj", x).view(B, L, heads, hd).transpose(1, 2)
     v = lin("v_proj", x).view(B, L, heads, hd).transpose(1, 2)
+    if xpos_scale_base is not None:  # multihead_attention.py:112-118 (offset 0)
+        k = xpos(k.reshape(B * heads, L, hd), xpos_scale_base, downscale=True).view(B, heads, L, hd)
+        q = xpos(q.reshape(B * heads, L, hd), xpos_scale_base, downscale=False).view(B, heads, L, hd)
     s = q @ k.transpose(-1, -2)
     if key_pad is not None:
         s = s.masked_fill(key_pad.bool()[:, None, None, :], float("-inf"))
@@ -281,23 +303,23 @@ def m2_ffn(sd, pfx, x, way, eps=1e-5):
     return g @ sd[f"{pfx}{way}.fc2.weight"].t() + sd[f"{pfx}{way}.fc2.bias"]
 
 
-def m2_encoder_layer(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
+def m2_encoder_layer(sd, pfx, x, heads, way, key_pad=None, eps=1e-5, xpos_scale_base=None):
     """EncoderLayer.forward, vlmo/torchscale/architecture/encoder.py:113-168 with normalize_before=True, subln=True,
     alpha = 1 (no deepnorm), dropout / drop_path 0, no MoE."""
     h = layer_norm(x, sd[f"{pfx}self_attn_layer_norm.{way}.weight"], sd[f"{pfx}self_attn_layer_norm.{way}.bias"], eps)
-    x = x + m2_attention(sd, pfx + "self_attn.", h, heads, way, key_pad, eps)
+    x = x + m2_attention(sd, pfx + "self_attn.", h, heads, way, key_pad, eps, xpos_scale_base)
     h = layer_norm(x, sd[f"{pfx}final_layer_norm.{way}.weight"], sd[f"{pfx}final_layer_norm.{way}.bias"], eps)
     return x + m2_ffn(sd, pfx + "ffn.", h, way, eps)
 
 
-def m2_encoder(sd, pfx, x, heads, way, key_pad=None, eps=1e-5):
+def m2_encoder(sd, pfx, x, heads, way, key_pad=None, eps=1e-5, xpos_scale_base=None):
     """Encoder.forward, architecture/encoder.py:388-482, from token embeddings `x` that already carry positions:
     zero the padded rows (:440), the layers, final `layer_norm` (:469-470; normalize_output=True)."""
     if key_pad is not None:
         x = x * (1 - key_pad.unsqueeze(-1).to(x.dtype))
     n_layers = 1 + max(int(k[len(pfx) :].split(".")[1]) for k in sd if k.startswith(pfx + "layers."))
     for i in range(n_layers):
-        x = m2_encoder_layer(sd, f"{pfx}layers.{i}.", x, heads, way, key_pad, eps)
+        x = m2_encoder_layer(sd, f"{pfx}layers.{i}.", x, heads, way, key_pad, eps, xpos_scale_base)
     return layer_norm(x, sd[f"{pfx}layer_norm.{way}.weight"], sd[f"{pfx}layer_norm.{way}.bias"], eps)
 
 
@@ -318,22 +340,22 @@ def m2_text_embed(sd, pfx, ids):
     return sd[pfx + "text_embed.weight"][ids] + sd[pfx + "encoder.embed_positions.B.weight"][2 : L + 2]
 
 
-def m2_infer_image(sd, image, heads):
+def m2_infer_image(sd, image, heads, xpos_scale_base=None):
     """VLMo.infer_image, vlmo/modules/vlmo_module.py:364-405 (the caller passes the already inception-normalised
     tensor, :385): backbone with expert A, backbone_vl with expert A (split −1), ITC heads on the CLS rows, L2-norm."""
-    h = m2_encoder(sd, "backbone.encoder.", m2_vision_embed(sd, "backbone.", image), heads, "A")
-    hv = m2_encoder(sd, "backbone_vl.", h, heads, "A")
+    h = m2_encoder(sd, "backbone.encoder.", m2_vision_embed(sd, "backbone.", image), heads, "A", xpos_scale_base=xpos_scale_base)
+    hv = m2_encoder(sd, "backbone_vl.", h, heads, "A", xpos_scale_base=xpos_scale_base)
     f = h[:, 0] @ sd["itc_image_proj.fc.weight"].t()
     fv = hv[:, 0] @ sd["itc_vl_image_proj.fc.weight"].t()
     return h, f / f.norm(dim=-1, keepdim=True), fv / fv.norm(dim=-1, keepdim=True)
 
 
-def m2_infer_text(sd, ids, masks, heads):
+def m2_infer_text(sd, ids, masks, heads, xpos_scale_base=None):
     """VLMo.infer_text, vlmo_module.py:323-362: backbone with expert B and key padding = 1 − text_masks; backbone_vl
     with expert A (split −1, :343) on the language hiddens; ITC heads on CLS, L2-norm."""
     pad = 1 - masks
-    h = m2_encoder(sd, "backbone.encoder.", m2_text_embed(sd, "backbone.", ids), heads, "B", pad)
-    hv = m2_encoder(sd, "backbone_vl.", h, heads, "A", pad)
+    h = m2_encoder(sd, "backbone.encoder.", m2_text_embed(sd, "backbone.", ids), heads, "B", pad, xpos_scale_base=xpos_scale_base)
+    hv = m2_encoder(sd, "backbone_vl.", h, heads, "A", pad, xpos_scale_base=xpos_scale_base)
     f = h[:, 0] @ sd["itc_text_proj.fc.weight"].t()
     fv = hv[:, 0] @ sd["itc_vl_text_proj.fc.weight"].t()
     return h, f / f.norm(dim=-1, keepdim=True), fv / fv.norm(dim=-1, keepdim=True)

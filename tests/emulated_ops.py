@@ -179,6 +179,19 @@ def masked_mean_bwd(dy, pad, inv, P):
     return (dy.float()[:, None, :] * (keep * inv[:, None])[:, :, None]).to(BF)
 
 
+def xpos_apply(qkv, tables, B, L, H, hd, backward=False, q_off=0, k_off=None):
+    W = H * hd
+    k_off = W if k_off is None else k_off
+    q_cos, q_sin, k_cos, k_sin = tables
+    sign = -1.0 if backward else 1.0
+    for off, cs, sn in ((q_off, q_cos, q_sin), (k_off, k_cos, k_sin)):
+        x = qkv[:, off:off + W].float().reshape(B, L, H, hd // 2, 2)
+        c, s = cs[None, :, None, :], sn[None, :, None, :] * sign
+        out = torch.stack((c * x[..., 0] - s * x[..., 1], c * x[..., 1] + s * x[..., 0]), dim=-1)
+        qkv[:, off:off + W] = out.reshape(B * L, W).to(qkv.dtype)
+    return qkv
+
+
 def gather_rows(src, ids):
     ok = (ids >= 0) & (ids < src.shape[0])
     out = src[ids.clamp(0, src.shape[0] - 1)].clone()

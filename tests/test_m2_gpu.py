@@ -77,7 +77,8 @@ def _build(fx, checkpoint=False, keep=0):
 
     c = fx["config"]
     m = M2Encoder(image_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"],
-                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"])
+                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"],
+                  max_source_positions=c.get("max_source_positions", 1024), xpos_rel_pos=c.get("xpos", False))
     missing, unexpected = m.load_state_dict(fx["state_dict"], strict=False)
     assert not unexpected and all(k.startswith(("norm.", "pooler.")) for k in missing)
     m = m.cuda().to(BF).train()
@@ -86,20 +87,20 @@ def _build(fx, checkpoint=False, keep=0):
     return m
 
 
-def _oracle(sd_src, image, ids, masks, heads, device="cpu", dtype=torch.float32):
+def _oracle(sd_src, image, ids, masks, heads, device="cpu", dtype=torch.float32, xpos=None):
     sd = {k: (v.detach().to(BF).to(dtype).to(device).requires_grad_(True) if torch.is_floating_point(v) else v.to(device)) for k, v in sd_src.items()}
-    h_i, f_i, fv_i = restated.m2_infer_image(sd, image.to(BF).to(dtype).to(device), heads)
-    h_t, f_t, fv_t = restated.m2_infer_text(sd, ids.to(device), masks.to(device), heads)
+    h_i, f_i, fv_i = restated.m2_infer_image(sd, image.to(BF).to(dtype).to(device), heads, xpos)
+    h_t, f_t, fv_t = restated.m2_infer_text(sd, ids.to(device), masks.to(device), heads, xpos)
     sdf = {k: v.float() for k, v in sd.items() if k.startswith("logit")}
     loss = restated.m2_itc_loss(sdf, f_i.float(), f_t.float(), fv_i.float(), fv_t.float())
     loss.backward()
     return sd, (h_i, h_t, f_i, f_t, fv_i, fv_t), loss
 
 
-def _check_against(m, fx_sd, image, ids, masks, heads, golden=None):
-    sd16, (o_hi, o_ht, o_fi, o_ft, o_fvi, o_fvt), o_loss = _oracle(fx_sd, image, ids, masks, heads)
+def _check_against(m, fx_sd, image, ids, masks, heads, golden=None, xpos=None, min_grads=60):
+    sd16, (o_hi, o_ht, o_fi, o_ft, o_fvi, o_fvt), o_loss = _oracle(fx_sd, image, ids, masks, heads, xpos=xpos)
     # calibrator: the same oracle arithmetic in bf16 torch eager on the GPU (the reference modules after .cuda().bfloat16())
-    sdb, _, _ = _oracle(fx_sd, image, ids, masks, heads, device="cuda", dtype=BF)
+    sdb, _, _ = _oracle(fx_sd, image, ids, masks, heads, device="cuda", dtype=BF, xpos=xpos)
     img = m.infer_image({"image": [image.cuda()]})
     txt = m.infer_text({"text_ids": ids.cuda(), "text_masks": masks.cuda()})
     assert img["cls_feats"].dtype == BF and img["cls_feats"].is_cuda
@@ -137,7 +138,7 @@ def _check_against(m, fx_sd, image, ids, masks, heads, golden=None):
         worst[n] = rel_l2(p.grad, ref)
         eager[n] = rel_l2(sdb[n].grad, ref)
         assert worst[n] < max(3e-2, 2.0 * eager[n]), (n, worst[n], eager[n])
-    assert with_grad > 60
+    assert with_grad > min_grads
     med = sorted(worst.values())[len(worst) // 2]
     med_eager = sorted(eager.values())[len(eager) // 2]
     assert med < max(2.5e-2, 2.0 * med_eager), (med, med_eager)
@@ -149,6 +150,41 @@ def test_m2_encoder_matches_reference_golden(golden_dir, checkpoint, keep):
     fx = torch.load(os.path.join(golden_dir, "m2_tiny.pt"), weights_only=False)
     m = _build(fx, checkpoint, keep)
     _check_against(m, fx["state_dict"], fx["image"], fx["ids"], fx["masks"], fx["config"]["heads"], golden=fx)
+
+
+@pytest.mark.parametrize("checkpoint", [False, True])
+def test_m2_encoder_xpos_matches_reference_golden(golden_dir, checkpoint):
+    """args.xpos_rel_pos = True: XPOS rotary embedding applied in place to q / k of the fused projection (the optional RoPE of the path),
+    forward and transposed in backward — vs the golden vectors of the unmodified reference run with XPOS (odd lengths 17 / 11)."""
+    fx = torch.load(os.path.join(golden_dir, "m2_tiny_xpos.pt"), weights_only=False)
+    m = _build(fx, checkpoint)
+    _check_against(m, fx["state_dict"], fx["image"], fx["ids"], fx["masks"], fx["config"]["heads"], golden=fx, xpos=512, min_grads=40)
+
+
+def test_xpos_apply_kernel_matches_reference_expression():
+    """b200mm_xpos_apply vs the reference's apply_rotary_pos_emb expression (oracle restated.xpos), forward and the transposed map."""
+    from b200mm import ops
+    from b200mm.modules.beit3 import xpos_tables
+
+    torch.manual_seed(0)
+    B, L, H, hd = 3, 197, 4, 64
+    W = H * hd
+    qkv = torch.randn(B * L, 3 * W, device="cuda").to(BF)
+    tabs = xpos_tables(L, hd, 512, "cuda")
+    ref = qkv.float().cpu().clone()
+    for sec, down in ((0, False), (1, True)):
+        x = ref[:, sec * W:(sec + 1) * W].reshape(B, L, H, hd).transpose(1, 2).reshape(B * H, L, hd)
+        y = restated.xpos(x, 512, downscale=down).view(B, H, L, hd).transpose(1, 2).reshape(B * L, W)
+        ref[:, sec * W:(sec + 1) * W] = y
+    out = ops.xpos_apply(qkv.clone(), tabs, B, L, H, hd)
+    assert torch.equal(out[:, 2 * W:], qkv[:, 2 * W:])  # v untouched
+    assert float((out.float().cpu() - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max())
+    # transposed map: <R x, g> == <x, R^T g>
+    g = torch.randn_like(qkv)
+    rt_g = ops.xpos_apply(g.clone(), tabs, B, L, H, hd, backward=True)
+    lhs = float((out.float()[:, :2 * W] * g.float()[:, :2 * W]).sum())
+    rhs = float((qkv.float()[:, :2 * W] * rt_g.float()[:, :2 * W]).sum())
+    assert abs(lhs - rhs) < 2e-2 * max(abs(lhs), 1.0), (lhs, rhs)
 
 
 def test_m2_encoder_hd64_matches_oracle():

@@ -17,15 +17,17 @@ def rel_l2(got, ref):
     return float((got - ref).norm() / ref.norm().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("checkpoint,keep", [(False, 0), (True, 0), (False, 2)])
-def test_m2_glue_reproduces_reference_golden(golden_dir, checkpoint, keep):
+@pytest.mark.parametrize("name,checkpoint,keep", [("m2_tiny.pt", False, 0), ("m2_tiny.pt", True, 0), ("m2_tiny.pt", False, 2),
+                                                  ("m2_tiny_xpos.pt", False, 0), ("m2_tiny_xpos.pt", True, 0)])
+def test_m2_glue_reproduces_reference_golden(golden_dir, name, checkpoint, keep):
     from b200mm.modules import M2Encoder
     from oracle import restated
 
-    fx = torch.load(os.path.join(golden_dir, "m2_tiny.pt"), weights_only=False)
+    fx = torch.load(os.path.join(golden_dir, name), weights_only=False)
     c = fx["config"]
     m = M2Encoder(image_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"],
-                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"])
+                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"],
+                  max_source_positions=c.get("max_source_positions", 1024), xpos_rel_pos=c.get("xpos", False))
     m.load_state_dict(fx["state_dict"], strict=False)
     m = m.to(BF).train()
     m.set_grad_checkpointing(checkpoint)
@@ -52,4 +54,4 @@ def test_m2_glue_reproduces_reference_golden(golden_dir, checkpoint, keep):
             continue
         n_checked += 1
         assert rel_l2(p.grad, ref) < 6e-2, (n, rel_l2(p.grad, ref))
-    assert n_checked > 60
+    assert n_checked > 40
