@@ -49,6 +49,15 @@ def xpos_tables(L, head_dim, scale_base=512, device="cpu"):
     return tuple(t.float().contiguous().to(device) for t in out)
 
 
+class XPOS(nn.Module):
+    """State-dict twin of the reference XPOS module (xpos_relative_position.py:35-40): the registered buffer `scale` [head_dim/2]."""
+
+    def __init__(self, head_dim, scale_base=512):
+        super().__init__()
+        self.head_dim, self.scale_base = head_dim, scale_base
+        self.register_buffer("scale", (torch.arange(0, head_dim, 2) + 0.4 * head_dim) / (1.4 * head_dim))
+
+
 class MultiwayNetwork(nn.Module):
     """Two copies of a parameter container: .A (vision expert) and .B (language expert) — multiway_network.py:24-45."""
 
@@ -81,6 +90,8 @@ class MultiheadAttention(nn.Module):
         self.embed_dim, self.num_heads = embed_dim, num_heads
         self.xpos_rel_pos, self.xpos_scale_base = xpos_rel_pos, xpos_scale_base
         self._xpos_cache = {}
+        if xpos_rel_pos:
+            self.xpos = XPOS(embed_dim // num_heads, xpos_scale_base)
         self.head_dim = embed_dim // num_heads
         self.scaling = self.head_dim ** -0.5
         lin = lambda: nn.Linear(embed_dim, embed_dim, bias=True)  # noqa: E731
@@ -90,7 +101,7 @@ class MultiheadAttention(nn.Module):
         self.out_proj = MultiwayNetwork(lin)
         self.inner_attn_ln = MultiwayNetwork(lambda: nn.LayerNorm(embed_dim, eps=eps))
 
-    def xpos(self, L, device):
+    def xpos_tables_for(self, L, device):
         """XPOS tables for sequences of length L (None when args.xpos_rel_pos is off, the shipped default)."""
         if not self.xpos_rel_pos:
             return None
@@ -123,7 +134,7 @@ class EncoderLayer(nn.Module):
 
     def forward_tokens(self, x2d, key_bias, B, L, split_position):
         return Fn.M2EncoderLayerFn.apply(x2d, *self.layer_params(split_position), key_bias, B, L, self.self_attn.num_heads, self.eps,
-                                         self.checkpoint, self.keep_act, self.self_attn.xpos(L, x2d.device))
+                                         self.checkpoint, self.keep_act, self.self_attn.xpos_tables_for(L, x2d.device))
 
 
 class PositionalEmbedding(nn.Embedding):

@@ -93,15 +93,17 @@ def test_golden_state_dict_loads_strict(golden_dir):
     assert not missing and not unexpected
 
 
-def test_m2_encoder_state_dict_keys_match_reference(golden_dir):
-    """M2Encoder carries the reference's parameter names and shapes (prj/M2_Encoder: BEiT3 + backbone_vl Encoder + ITC heads),
-    checked against the state dict of the unmodified reference classes stored in tests/golden/m2_tiny.pt."""
+@pytest.mark.parametrize("name", ["m2_tiny.pt", "m2_tiny_xpos.pt"])
+def test_m2_encoder_state_dict_keys_match_reference(golden_dir, name):
+    """M2Encoder carries the reference's parameter / buffer names and shapes (prj/M2_Encoder: BEiT3 + backbone_vl Encoder + ITC heads;
+    with XPOS also `self_attn.xpos.scale`), checked against the state dicts of the unmodified reference classes in tests/golden/."""
     from b200mm.modules import M2Encoder
 
-    fx = torch.load(os.path.join(golden_dir, "m2_tiny.pt"), weights_only=False)
+    fx = torch.load(os.path.join(golden_dir, name), weights_only=False)
     c = fx["config"]
     m = M2Encoder(image_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"],
-                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"])
+                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"],
+                  max_source_positions=c.get("max_source_positions", 1024), xpos_rel_pos=c.get("xpos", False))
     ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     ref = {k: tuple(v.shape) for k, v in fx["state_dict"].items()}
     assert set(ref) <= set(ours), sorted(set(ref) - set(ours))[:5]
@@ -114,6 +116,7 @@ def test_m2_encoder_state_dict_keys_match_reference(golden_dir):
         m2 = ref_loader.load_m2()
         args = m2.EncoderConfig(img_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], multiway=True, no_output_layer=True,
                                 encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"], encoder_layers=c["layers"],
-                                encoder_ffn_embed_dim=4 * c["W"], max_text_len=c["L"])
+                                encoder_ffn_embed_dim=4 * c["W"], max_text_len=c["L"], xpos_rel_pos=c.get("xpos", False),
+                                max_source_positions=c.get("max_source_positions", 1024))
         live = {"backbone." + k: tuple(v.shape) for k, v in m2.BEiT3(args).state_dict().items()}
         assert all(ours[k] == s for k, s in live.items())
