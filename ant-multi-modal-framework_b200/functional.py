@@ -44,50 +44,62 @@ def _wgrad(dy, x):
 # ======================================================================================================================
 # ViT residual attention block (pre-LN) — antmmf/modules/vision/backbone/clip/model.py:227-256
 # ======================================================================================================================
-def _vit_block_forward(x, p, B, L, H, eps):
+def _vit_block_forward(x, p, B, L, H, eps, keep_ln=False):
     (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b) = p
     W = x.shape[1]
     h1, _, mean1, rstd1 = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
     qkv = ops.gemm(h1, in_w, bias=in_b)
-    del h1
+    if not keep_ln:
+        del h1
+        h1 = None
     o, lse = ops.attention_fwd(qkv, B, L, H, W // H)
     x_mid = ops.gemm(o, out_w, bias=out_b, residual=x)
     h2, _, mean2, rstd2 = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
     g, u = ops.gemm(h2, fc_w, bias=fc_b, act=ACT_QUICKGELU, aux_out=True)
-    del h2
+    if not keep_ln:
+        del h2
+        h2 = None
     y = ops.gemm(g, proj_w, bias=proj_b, residual=x_mid)
-    return y, (mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u), g
+    return y, (mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u), g, (h1, h2)
 
 
 class VitBlockFn(Function):
+    """Memory-for-time knobs (both default off): `keep_act` keeps the activated MLP hidden g (8·T·W bytes per block; since the dgrad GEMM
+    emits g next to du it only saves that epilogue's extra store, ≈ 0.08 ms per block at T = 263 168), `keep_ln` keeps both LayerNorm
+    outputs (4·T·W bytes per block) and saves the two LN recomputes of the backward (≈ 0.37 ms per block): twice the time per byte."""
+
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b, B, L, H, eps, checkpoint,
-                keep_act):
+                keep_act, keep_ln=False):
         p = (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b)
-        y, saved, g = _vit_block_forward(x, p, B, L, H, eps)
         keep_act = bool(keep_act) and not checkpoint
-        ctx.meta = (B, L, H, eps, checkpoint, keep_act)
+        keep_ln = bool(keep_ln) and not checkpoint
+        y, saved, g, hs = _vit_block_forward(x, p, B, L, H, eps, keep_ln)
+        ctx.meta = (B, L, H, eps, checkpoint, keep_act, keep_ln)
+        extra = ((g,) if keep_act else ()) + (hs if keep_ln else ())
         if checkpoint:
             ctx.save_for_backward(x, *p)
-        elif keep_act:  # memory for time: the activated MLP hidden is kept instead of being recomputed in backward
-            ctx.save_for_backward(x, *p, *saved, g)
         else:
-            ctx.save_for_backward(x, *p, *saved)
+            ctx.save_for_backward(x, *p, *saved, *extra)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        B, L, H, eps, checkpoint, keep_act = ctx.meta
+        B, L, H, eps, checkpoint, keep_act, keep_ln = ctx.meta
         t = ctx.saved_tensors
         x, p = t[0], t[1:13]
         (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b) = p
-        g = None
+        g = h1 = h2 = None
         if checkpoint:
-            _, saved, g = _vit_block_forward(x, p, B, L, H, eps)
+            _, saved, g, _ = _vit_block_forward(x, p, B, L, H, eps)
         else:
             saved = t[13:22]
+            k = 22
             if keep_act:
-                g = t[22]
+                g = t[k]
+                k += 1
+            if keep_ln:
+                h1, h2 = t[k], t[k + 1]
         mean1, rstd1, qkv, o, lse, x_mid, mean2, rstd2, u = saved
         W = x.shape[1]
         dy = dy.contiguous()
@@ -101,7 +113,8 @@ class VitBlockFn(Function):
         d_proj_w = _wgrad(dy, g)
         del g
         ops.rowsum_periodic(dy, vg[7])
-        h2, _, _, _ = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+        if h2 is None:
+            h2, _, _, _ = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
         d_fc_w = _wgrad(du, h2)
         del h2
         ops.rowsum_periodic(du, vg[6])
@@ -115,7 +128,8 @@ class VitBlockFn(Function):
         d_o = ops.gemm(dx_mid, out_w, b_mn=True)
         dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, L, H, W // H)
         del d_o
-        h1, _, _, _ = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
+        if h1 is None:
+            h1, _, _, _ = ops.layernorm_fwd(x, ln1_w, ln1_b, eps)
         d_in_w = _wgrad(dqkv, h1)
         del h1
         ops.rowsum_periodic(dqkv, vg[2])
@@ -124,7 +138,7 @@ class VitBlockFn(Function):
         dx = ops.layernorm_bwd(dh1, x, mean1, rstd1, ln1_w, vg[0], vg[1], dadd=dx_mid)
         d_ln1_w, d_ln1_b, d_in_b, d_out_b, d_ln2_w, d_ln2_b, d_fc_b, d_proj_b = vg.finish()
         return (dx, d_ln1_w, d_ln1_b, d_in_w, d_in_b, d_out_w, d_out_b, d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, d_proj_w, d_proj_b,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 # ======================================================================================================================

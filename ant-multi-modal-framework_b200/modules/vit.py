@@ -48,6 +48,7 @@ class ResidualAttentionBlock(nn.Module):
         self.ln_2 = nn.LayerNorm(d_model)
         self.checkpoint = False
         self.keep_act = False
+        self.keep_ln = False
 
     def block_params(self):
         return tuple(_bf16(p) for p in (self.ln_1.weight, self.ln_1.bias, self.attn.in_proj_weight, self.attn.in_proj_bias,
@@ -55,7 +56,7 @@ class ResidualAttentionBlock(nn.Module):
                                         self.mlp.c_fc.weight, self.mlp.c_fc.bias, self.mlp.c_proj.weight, self.mlp.c_proj.bias))
 
     def forward_tokens(self, x2d, B, L):
-        return Fn.VitBlockFn.apply(x2d, *self.block_params(), B, L, self.n_head, self.ln_1.eps, self.checkpoint, self.keep_act)
+        return Fn.VitBlockFn.apply(x2d, *self.block_params(), B, L, self.n_head, self.ln_1.eps, self.checkpoint, self.keep_act, self.keep_ln)
 
 
 class Transformer(nn.Module):
@@ -90,6 +91,12 @@ class VisionTransformer(nn.Module):
         it from the pre-activation (2 bytes * 4 * width per token and block of extra memory; saves one HBM pass per block)."""
         for i, blk in enumerate(self.transformer.resblocks):
             blk.keep_act = i < n_blocks
+
+    def set_keep_layernorm(self, n_blocks):
+        """Keep both LayerNorm outputs (2 x width per token, 4*width bytes) of the first `n_blocks` blocks for backward instead of
+        recomputing them: half the memory of `set_keep_activation` per block and more time saved (two HBM passes per block)."""
+        for i, blk in enumerate(self.transformer.resblocks):
+            blk.keep_ln = i < n_blocks
 
     def forward_features(self, x: torch.Tensor):
         """[B, 3, R, R] -> token matrix [B*L, width] after the last block (no ln_post)."""

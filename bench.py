@@ -146,7 +146,7 @@ class _M2Step(torch.nn.Module):
         return self.m2.itc_loss(image, text, (text != 0).long(), group)
 
 
-def build_model(name, device, ckpt_every, keep_act=0):
+def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0):
     from b200mm.modules import CNCLIP, CONFIGS, M2_CONFIGS, M2Encoder
 
     if name == "base_vtp-ViT-B-16":
@@ -187,6 +187,8 @@ def build_model(name, device, ckpt_every, keep_act=0):
         model.visual.set_grad_checkpointing(True, every=ckpt_every)
     if keep_act > 0:
         model.visual.set_keep_activation(keep_act)
+    if keep_ln > 0:
+        model.visual.set_keep_layernorm(keep_ln)
     return model, cfg
 
 
@@ -219,7 +221,7 @@ def run_ours(args):
     b200mm._lib.check(b200mm._lib.load().b200mm_check_device(), "b200mm_check_device")
 
     B, L = args.batch, args.seq_len
-    model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act)
+    model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act, args.keep_ln)
     res = cfg["image_resolution"]
     step_mod = TrainStep(model)
     if world > 1 and args.micro_batch == 0:
@@ -259,13 +261,14 @@ def run_ours(args):
             step(image_d, text_d)
     except torch.OutOfMemoryError:
         # the keep-activation policy is a memory-for-time knob: fall back to recomputing every block's activated hidden
-        if args.keep_act == 0:
+        if (args.keep_act == 0 and args.keep_ln == 0) or not hasattr(model, "visual"):
             raise
         for p in model.parameters():
             p.grad = None
         torch.cuda.empty_cache()
-        args.keep_act = 0
+        args.keep_act = args.keep_ln = 0
         model.visual.set_keep_activation(0)
+        model.visual.set_keep_layernorm(0)
         for _ in range(args.warmup):
             step(image_d, text_d)
     barrier()
@@ -340,7 +343,7 @@ def run_ours(args):
                                     f"prj/M2_Encoder {args.model} (BEiT-3 multiway): infer_image + infer_text + symmetric ITC on both head pairs, fwd + bwd"),
                        "model": args.model, "per_gpu_batch": B, "global_batch": B * world, "image_res": res, "seq_len": L,
                        "parallelism": f"dp{world}" + (" + embedding all-gather / grad reduce-scatter, DDP grad all-reduce in the timed region" if world > 1 else ""),
-                       "dropout": 0.0, "recompute": f"GradCache two-pass, micro-batch {args.micro_batch} (second forward not counted)" if args.micro_batch else f"checkpoint every {args.ckpt_every} ViT block(s)" if args.ckpt_every else f"none (LN outputs recomputed; activated MLP hidden recomputed in {max(0, cfg['vision_layers'] - args.keep_act)} of {cfg['vision_layers']} ViT blocks)",
+                       "dropout": 0.0, "recompute": f"GradCache two-pass, micro-batch {args.micro_batch} (second forward not counted)" if args.micro_batch else f"checkpoint every {args.ckpt_every} ViT block(s)" if args.ckpt_every else f"none (selective save: LN outputs recomputed in {max(0, cfg['vision_layers'] - args.keep_ln)} and the activated MLP hidden in {max(0, cfg['vision_layers'] - args.keep_act)} of {cfg['vision_layers']} ViT blocks)",
                        "l2_policy": "inputs and activations (>= 0.5 GB per tensor) exceed the 126 MB L2; no flush needed",
                        "loss": round(loss_val, 5), "peak_mem_gib": round(peak_mem, 1)},
             "e2e": {"value": round(e2e_val, 2), "unit": "pairs/s", "ms_per_step": round(e2e_ms, 3),
@@ -486,7 +489,8 @@ def main():
     ap.add_argument("--seq-len", type=int, default=77)
     ap.add_argument("--ckpt-every", type=int, default=0, help="re-run every k-th ViT block in backward (0 = never)")
     ap.add_argument("--micro-batch", type=int, default=0, help="> 0: run the step through the GradCache two-pass driver with this micro-batch")
-    ap.add_argument("--keep-act", type=int, default=8, help="ViT blocks that keep the activated MLP hidden instead of recomputing it (memory for time)")
+    ap.add_argument("--keep-act", type=int, default=0, help="ViT blocks that keep the activated MLP hidden instead of recomputing it (memory for time)")
+    ap.add_argument("--keep-ln", type=int, default=16, help="ViT blocks that keep both LayerNorm outputs instead of recomputing them (memory for time)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU-baseline sample (fp32 eager needs ~0.6 GB of host RAM per pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="write gpurun_out/op_profile_b<B>.json (per-op CUDA-event breakdown)")

@@ -1,0 +1,50 @@
+"""Host logic of the headline path (CNCLIP: ViT + BERT towers, block-level autograd glue with its save / recompute policies) without a
+GPU: b200mm.modules.CNCLIP over the torch stand-ins of the kernels (tests/emulated_ops.py) must reproduce the golden vectors of the
+unmodified reference for every memory policy — plain, block checkpointing, keep-activation, keep-LayerNorm."""
+import os
+
+import pytest
+import torch
+
+from oracle import restated
+from tests import emulated_ops
+
+BF = torch.bfloat16
+
+
+def rel_l2(got, ref):
+    got, ref = got.detach().float(), ref.detach().float()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("name", ["cnclip_tiny.pt", "cnclip_tiny_h80.pt"])
+@pytest.mark.parametrize("policy", ["plain", "checkpoint", "keep_act", "keep_ln", "keep_both"])
+def test_cnclip_glue_reproduces_reference_golden(golden_dir, name, policy):
+    from b200mm.modules import CNCLIP
+
+    fx = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    m = CNCLIP(**fx["config"])
+    m.load_state_dict(fx["state_dict"])
+    m = m.to(BF).train()
+    m.set_grad_checkpointing(policy == "checkpoint")
+    if policy in ("keep_act", "keep_both"):
+        m.visual.set_keep_activation(1)
+    if policy in ("keep_ln", "keep_both"):
+        m.visual.set_keep_layernorm(2)
+    with emulated_ops.patched():
+        img, txt = m.encode_normalized(fx["image"].to(BF), fx["text"])
+        assert rel_l2(img, fx["image_features"]) < 2e-2 and rel_l2(txt, fx["text_features"]) < 2e-2
+        logits = m.logit_scale.float().exp() * img.float() @ txt.float().t()
+        loss = restated.symmetric_info_nce(logits)
+        assert abs(float(loss) - float(fx["loss"])) < 3e-2 * float(fx["loss"])
+        loss.backward()
+    checked = 0
+    for n, p in m.named_parameters():
+        ref = fx["grads"].get(n)
+        if ref is None or float(ref.abs().max()) < 1e-5 or n == "logit_scale":
+            continue
+        assert p.grad is not None, n
+        assert rel_l2(p.grad, ref) < 8e-2, (n, policy, rel_l2(p.grad, ref))
+        checked += 1
+    assert checked > 40
+    assert float(m.bert.embeddings.word_embeddings.weight.grad[0].abs().max()) == 0.0  # padding_idx row

@@ -314,3 +314,27 @@ def test_video_heads_frame_pooling_matches_reference_arithmetic():
     t = video.forward_text_encoder(FakeText(), torch.zeros(4, 6, dtype=torch.long, device="cuda"), torch.ones(4, 6, device="cuda"))
     assert set(t) == {"sequence_output", "pooled_output", "input_mask", "words_importance"} and t["words_importance"] is None
     assert float((t["pooled_output"].float().norm(dim=-1) - 1).abs().max()) < 1e-2
+
+
+def test_memory_policies_give_the_same_step(golden_dir):
+    """keep-activation / keep-LayerNorm / block checkpointing only change WHAT is kept for backward: loss identical, gradients equal up to
+    the order of the fp32 atomics that accumulate the small vector gradients."""
+    fx = torch.load(os.path.join(golden_dir, "cnclip_tiny.pt"), weights_only=False)
+    image, text = fx["image"].cuda(), fx["text"].cuda()
+    results = {}
+    for policy in ["plain", "keep_ln", "keep_act", "keep_both", "checkpoint"]:
+        m, _ = _build(fx, checkpoint=(policy == "checkpoint"))
+        if policy in ("keep_ln", "keep_both"):
+            m.visual.set_keep_layernorm(2)
+        if policy in ("keep_act", "keep_both"):
+            m.visual.set_keep_activation(1)
+        loss = m.contrastive_loss(image, text)
+        loss.backward()
+        results[policy] = (float(loss), {n: p.grad.float().clone() for n, p in m.named_parameters()})
+    base_loss, base = results["plain"]
+    for policy, (l, grads) in results.items():
+        assert l == base_loss, (policy, l, base_loss)
+        for n, g in grads.items():
+            if float(base[n].abs().max()) < 1e-6:
+                continue
+            assert rel_l2(g, base[n]) < 1e-2, (policy, n, rel_l2(g, base[n]))
