@@ -333,8 +333,10 @@ def test_memory_policies_give_the_same_step(golden_dir):
         results[policy] = (float(loss), {n: p.grad.float().clone() for n, p in m.named_parameters()})
     base_loss, base = results["plain"]
     for policy, (l, grads) in results.items():
-        assert l == base_loss, (policy, l, base_loss)
+        assert abs(l - base_loss) <= 1e-5 * abs(base_loss), (policy, l, base_loss)  # the loss is summed with fp32 atomics (order varies)
         for n, g in grads.items():
             if float(base[n].abs().max()) < 1e-6:
                 continue
-            assert rel_l2(g, base[n]) < 1e-2, (policy, n, rel_l2(g, base[n]))
+            # keep_act reuses the forward's act(fp32 accumulator), the other policies recompute act(bf16-rounded pre-activation): one bf16
+            # rounding apart in the c_proj weight gradient; everything else differs only by atomic order
+            assert rel_l2(g, base[n]) < (3e-2 if "keep_act" in policy or policy == "keep_both" else 1e-2), (policy, n, rel_l2(g, base[n]))
