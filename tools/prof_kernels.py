@@ -25,7 +25,7 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     y, _, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5)
     dw = torch.zeros(W, device="cuda")
     db = torch.zeros(W, device="cuda")
-    dx = ops.layernorm_bwd(dy, x, mean, rstd, w, dw, db, dadd=dy)
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, w, dw, db, dadd=y)  # a distinct tensor as the residual-branch gradient
     # MLP up-projection with fused bias + QuickGELU + pre-activation copy (K = 1024: the epilogue-heavy GEMM)
     g, u = ops.gemm(y, wfc, bias=bfc, act=ops.ACT_QUICKGELU, aux_out=True)
     # dgrad through the activation: du = (dy @ Wproj) * act'(u)
