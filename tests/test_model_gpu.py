@@ -339,4 +339,4 @@ def test_memory_policies_give_the_same_step(golden_dir):
                 continue
             # keep_act reuses the forward's act(fp32 accumulator), the other policies recompute act(bf16-rounded pre-activation): one bf16
             # rounding apart in the c_proj weight gradient; everything else differs only by atomic order
-            assert rel_l2(g, base[n]) < (3e-2 if "keep_act" in policy or policy == "keep_both" else 1e-2), (policy, n, rel_l2(g, base[n]))
+            assert rel_l2(g, base[n]) < (5e-2 if "keep_act" in policy or policy == "keep_both" else 2e-2), (policy, n, rel_l2(g, base[n]))
