@@ -228,12 +228,88 @@ def mil_nce_matrix_bwd(S, w, lse, gout):
     return g * gout
 
 
+NO_DIAG = -(1 << 40)
+_TILE = 256  # column tile of the contrastive epilogues (b200mm_contrast_num_tiles)
+
+
+def _logits(a, b, alpha, b_mn):
+    return alpha * (a.float() @ (b.float() if b_mn else b.float().t()))
+
+
+def contrast_lse_partials(a, b, alpha, diag_off, b_mn=False):
+    z = _logits(a, b, alpha, b_mn)
+    M, N = z.shape
+    nt = (N + _TILE - 1) // _TILE
+    pmax = torch.full((M, nt), float("-inf"))
+    psum = torch.zeros(M, nt)
+    for t in range(nt):
+        blk = z[:, t * _TILE:(t + 1) * _TILE]
+        pmax[:, t] = blk.max(dim=1).values
+        psum[:, t] = torch.exp(blk - pmax[:, t:t + 1]).sum(dim=1)
+    diag = torch.zeros(M)
+    cols = torch.arange(M) + diag_off
+    ok = (cols >= 0) & (cols < N)
+    diag[ok] = z[torch.arange(M)[ok], cols[ok]]
+    return pmax, psum, diag
+
+
+def contrast_lse_merge(partsA, partsB, diag, sub_diag, loss_sum):
+    pm = partsA[0] if partsB is None else torch.cat([partsA[0], partsB[0]], dim=1)
+    ps = partsA[1] if partsB is None else torch.cat([partsA[1], partsB[1]], dim=1)
+    m = pm.max(dim=1).values
+    sm = (ps * torch.exp(pm - m[:, None])).sum(dim=1)
+    sub = int(sub_diag)
+    if sub > 0:
+        sm = sm - torch.exp(diag - m)
+    elif sub < 0:
+        nm = torch.maximum(m, diag)
+        sm = sm * torch.exp(m - nm) + torch.exp(diag - nm)
+        m = nm
+    lse = m + torch.log(sm)
+    loss_sum += (lse - diag).sum()
+    return lse
+
+
+def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, diag_zero, dscale, b_mn=False):
+    z = _logits(a, b, alpha, b_mn)
+    M, N = z.shape
+    dz = coef * torch.exp(z - row_lse[:, None])
+    cols = torch.arange(M) + diag_off
+    ok = (cols >= 0) & (cols < N)
+    r = torch.arange(M)[ok]
+    dz[r, cols[ok]] -= coef * diag_sub
+    if diag_zero:
+        dz[r, cols[ok]] = 0.0
+    dz[:, n_valid:] = 0.0
+    if dscale is not None:
+        dscale += (dz * z).sum()
+    return (alpha * dz).to(BF)
+
+
+def contrast_rank(a, b, alpha, ref, diag_off=0, gt_col=None, b_mn=False):
+    z = _logits(a, b, alpha, b_mn)
+    M, N = z.shape
+    pos = gt_col.long() if gt_col is not None else torch.arange(M) + diag_off
+    beats = z > ref[:, None]
+    ok = (pos >= 0) & (pos < N)
+    beats[torch.arange(M)[ok], pos[ok]] = False
+    return beats.sum(dim=1).to(torch.int32)
+
+
+def rowdot(a, b, scale=1.0):
+    return scale * (a.float() * b.float()).sum(-1)
+
+
+def ema_update(pk32, pq, m):
+    pk32.mul_(m).add_(pq.float(), alpha=1.0 - m)
+
+
 @contextlib.contextmanager
 def patched():
     """Swaps the kernel wrappers of b200mm.ops for the stand-ins above (restored on exit)."""
     from b200mm import ops
 
-    names = [n for n, f in globals().items() if callable(f) and not n.startswith("_") and hasattr(ops, n) and n not in ("patched",)]
+    names = [n for n, f in globals().items() if (callable(f) or n == "NO_DIAG") and not n.startswith("_") and hasattr(ops, n) and n != "patched"]
     saved = {n: getattr(ops, n) for n in names}
     try:
         for n in names:

@@ -34,14 +34,16 @@ def test_cnclip_glue_reproduces_reference_golden(golden_dir, name, policy):
     with emulated_ops.patched():
         img, txt = m.encode_normalized(fx["image"].to(BF), fx["text"])
         assert rel_l2(img, fx["image_features"]) < 2e-2 and rel_l2(txt, fx["text_features"]) < 2e-2
-        logits = m.logit_scale.float().exp() * img.float() @ txt.float().t()
-        loss = restated.symmetric_info_nce(logits)
+        loss = m.contrastive_loss(fx["image"].to(BF), fx["text"])  # the production fused-loss host code (b200mm.contrastive)
         assert abs(float(loss) - float(fx["loss"])) < 3e-2 * float(fx["loss"])
         loss.backward()
     checked = 0
     for n, p in m.named_parameters():
         ref = fx["grads"].get(n)
-        if ref is None or float(ref.abs().max()) < 1e-5 or n == "logit_scale":
+        if ref is None or float(ref.abs().max()) < 1e-5:
+            continue
+        if n == "logit_scale":  # scalar with heavy cancellation: absolute bound
+            assert abs(float(p.grad) - float(ref)) < 5e-2 * max(1.0, abs(float(ref))), (float(p.grad), float(ref))
             continue
         assert p.grad is not None, n
         assert rel_l2(p.grad, ref) < 8e-2, (n, policy, rel_l2(p.grad, ref))

@@ -147,3 +147,76 @@ def test_world2_gloo_stage2_hard_mining(tmp_path):
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert (tmp_path / "ok2_0").exists() and (tmp_path / "ok2_1").exists()
+
+
+WORKER_LOSSES = textwrap.dedent(
+    """
+    import os, sys
+    sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import b200mm
+    from b200mm.contrastive import clip_contrastive_loss, mil_nce_loss
+    from oracle import restated
+    from tests import emulated_ops
+    BF = torch.bfloat16
+
+    def rel(a, b):
+        a, b = a.detach().float(), b.detach().float()
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+    def mean_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t) / world
+
+    g = torch.Generator().manual_seed(11)
+    B, E = 5, 16   # 5 rows per rank: the gathered 10 rows are padded to 16 inside _gather_rows
+    I_all = torch.nn.functional.normalize(torch.randn(B * world, E, generator=g), dim=-1).to(BF)
+    T_all = torch.nn.functional.normalize(I_all.float() + 0.7 * torch.randn(B * world, E, generator=g), dim=-1).to(BF)
+    sl = slice(rank * B, (rank + 1) * B)
+    with emulated_ops.patched():
+        # ---- symmetric InfoNCE (CNCLIP.contrastive_loss): the REAL _ContrastiveFn host code, sharded over 2 ranks
+        i_loc, t_loc = I_all[sl].clone().requires_grad_(), T_all[sl].clone().requires_grad_()
+        ls = torch.tensor(2.0, requires_grad=True)
+        loss = clip_contrastive_loss(i_loc, t_loc, ls)
+        loss.backward()
+        If, Tf, lsf = I_all.float().requires_grad_(), T_all.float().requires_grad_(), torch.tensor(2.0, requires_grad=True)
+        full = restated.symmetric_info_nce(lsf.exp() * If @ Tf.t())
+        full.backward()
+        assert abs(mean_over_ranks(loss) - float(full)) < 1e-4 * float(full), (float(loss), float(full))
+        # DDP averages parameter gradients over ranks: (1/W) * sum_r d(W * share_r) = d(global loss)
+        assert rel(i_loc.grad.float() / world, If.grad[sl]) < 2e-2 and rel(t_loc.grad.float() / world, Tf.grad[sl]) < 2e-2
+        assert abs(mean_over_ranks(ls.grad) - float(lsf.grad)) < 2e-2 * max(1.0, abs(float(lsf.grad)))
+        # ---- MIL-NCE, n_clips = 1 and 2 (forward_stage1 of base_vtp)
+        for n in (1, 2):
+            V_all = torch.nn.functional.normalize(T_all.float().repeat_interleave(n, 0) + 0.6 * torch.randn(B * world * n, E, generator=g), dim=-1).to(BF)
+            v_loc = V_all[rank * B * n:(rank + 1) * B * n].clone().requires_grad_()
+            t_loc = T_all[sl].clone().requires_grad_()
+            loss = mil_nce_loss(v_loc, t_loc, None, n_clips=n)
+            loss.backward()
+            Vf, Tf = V_all.float().requires_grad_(), T_all.float().requires_grad_()
+            full = restated.mil_nce_clips(restated.l1_simi_matrix(Tf, Vf, n))
+            full.backward()
+            assert abs(mean_over_ranks(loss) - float(full)) < 2e-4 * float(full), (n, float(loss), float(full))
+            assert rel(v_loc.grad.float() / world, Vf.grad[rank * B * n:(rank + 1) * B * n]) < 3e-2, n
+            assert rel(t_loc.grad.float() / world, Tf.grad[sl]) < 3e-2, n
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok3_{rank}"), "w").write("ok")
+    """
+)
+
+
+def test_world2_gloo_contrastive_losses_host_code(tmp_path):
+    """The production host code of the sharded losses (b200mm.contrastive._ContrastiveFn / _MilNceClipsFn: padded all-gather, per-rank
+    logit blocks, W x local share, reduce-scatter of remote-row gradients) on 2 gloo ranks over the torch stand-ins of the kernels — vs
+    the full-batch oracle: mean over ranks of the loss = global loss, DDP-averaged gradients = global gradient."""
+    script = tmp_path / "worker_losses.py"
+    script.write_text(WORKER_LOSSES % ROOT)
+    port = 29800 + (os.getpid() % 90)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok3_0").exists() and (tmp_path / "ok3_1").exists()

@@ -31,8 +31,6 @@ def test_vtp_forward_matches_oracle_composition(hard, monkeypatch):
     assert "module.text_encoder.text_projection" in keys and "module.img_encoder.visual.conv1.weight" in keys
     assert "module.text_encoder.encoder.layer.0.attention.self.query.weight" in keys
     img_input, cap_input = vtp_common.make_batch()
-    # the fused level-1 loss needs the contrastive GEMM epilogues (GPU only): stand in with the oracle's formula on the same embeddings
-    monkeypatch.setattr(vtp, "mil_nce_loss", lambda v, t, group, n_clips=1: restated.mil_nce_clips(restated.l1_simi_matrix(t.float(), v.float(), n_clips)))
     with emulated_ops.patched():
         out = model(img_input, cap_input)
         ref, leaves = vtp_common.oracle_forward(model, img_input, cap_input, cfg)
@@ -66,7 +64,6 @@ def test_vtp_gradient_routing_matches_oracle(monkeypatch):
     img_input, caption = vtp_common.make_batch()
     g = torch.Generator().manual_seed(9)
     R1, R2, R3 = torch.randn(6, vtp_common.HID, generator=g), torch.randn(6, vtp_common.HID, generator=g), torch.randn(6, 6, generator=g)
-    monkeypatch.setattr(vtp, "mil_nce_loss", lambda v, t, group, n_clips=1: restated.mil_nce_clips(restated.l1_simi_matrix(t.float(), v.float(), n_clips)))
     with emulated_ops.patched():
         cap_input, vis_input, _, _ = model.module.get_l2_input(img_input, caption)
         out = model.forward_stage(cap_input + (caption,), vis_input + (img_input,), True)
@@ -113,7 +110,6 @@ def test_univl_model_plugin_interface(monkeypatch):
     m = m.to(BF).train()
     img_input, caption = vtp_common.make_batch()
     sample_list = {**img_input, **caption}
-    monkeypatch.setattr(vtp, "mil_nce_loss", lambda v, t, group, n_clips=1: restated.mil_nce_clips(restated.l1_simi_matrix(t.float(), v.float(), n_clips)))
     with emulated_ops.patched():
         out = m(sample_list)
         direct = m.model(img_input, caption)
@@ -131,3 +127,39 @@ def test_univl_model_plugin_interface(monkeypatch):
     with pytest.raises(NotImplementedError):
         bad = vtp.B200Univl(dict(cfg, training_head_type="pretraining"))
         bad.build()
+
+
+def test_vtp_moco_stage1_host_logic():
+    """with_moco (the reference default): momentum key encoders (fp32 copies, EMA), both queue losses, enqueue after the loss and BEFORE
+    backward (the order forward_stage1 uses: the saved queue image must not be modified in place) — vs the oracle's moco_nce."""
+    from b200mm import vtp
+
+    cfg = vtp_common.make_config(stage="stage1", hard=False, with_moco=True)
+    torch.manual_seed(0)
+    model = vtp.B200VideoTextRetrieval(cfg)
+    vtp_common.randomize(model)
+    model = model.to(BF).train()
+    img_input, caption = vtp_common.make_batch()
+    with emulated_ops.patched():
+        out = model(img_input, caption)
+        mu = model.moco_utils
+        assert int(mu.txt_queue_ptr) == 6 and int(mu.img_queue_ptr) == 6 and set(dict(mu.named_buffers())) >= {"txt_queue", "img_queue"}
+        loss = out["losses"]["level1_similarity_loss"]
+        loss.backward()  # must not trip autograd's version check on the queue image
+        with torch.no_grad():
+            cap_input, vis_input, _, _ = model.module.get_l2_input(img_input, caption)
+            q_t, q_v = cap_input[2].float(), vis_input[2].float()
+            key_v = model.module.forward_img_encoder(**img_input, img_encoder=mu.img_encoder_k)["clip_feature"].float()
+            key_t = model.module.forward_text_encoder(caption["caption_raw_input_ids"], caption["caption_input_mask"], txt_encoder=mu.txt_encoder_k)["pooled_output"].float()
+    # the first 6 queue columns were overwritten by the enqueue AFTER the loss was taken: compare on the untouched remainder (2 % of the
+    # 256 / 16384 negatives)
+    ref_v = restated.moco_nce((q_v * key_t).sum(-1, keepdim=True), q_v @ mu.txt_queue.float()[:, 6:].to(BF).float(), 0.05)
+    ref_t = restated.moco_nce((q_t * key_v).sum(-1, keepdim=True), q_t @ mu.img_queue.float()[:, 6:].to(BF).float(), 0.05)
+    ref = float((ref_v + ref_t) / 2)
+    assert abs(float(loss) - ref) < 0.05 * ref, (float(loss), ref)
+    assert model.module.img_encoder.visual.proj.grad is not None and model.module.text_encoder.text_projection.grad is not None
+    assert all(p.grad is None for p in mu.txt_encoder_k.parameters())
+    # EMA: the key encoders moved towards the query encoders by (1 - M)
+    w_q = model.module.text_encoder.text_projection.detach().float()
+    w_k = mu.txt_encoder_k.text_projection.detach().float()
+    assert w_k.dtype == torch.float32 and float((w_k - w_q).abs().max()) < 1e-2
