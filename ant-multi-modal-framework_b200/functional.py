@@ -584,3 +584,135 @@ class M2TextEmbedFn(Function):
         d_word = ops.cast_f32_bf16(acc)
         (d_pos,) = vg.finish()
         return d_word, None, d_pos.view(L, W), None
+
+
+# ======================================================================================================================
+# M²-Encoder layer in three pieces, for a multiway split INSIDE a sequence (fused vision + language input, split_position > 0:
+# multiway_network.py:38-45): the per-token parts run per expert on that expert's rows, attention runs on the joint sequence.
+# ======================================================================================================================
+class M2PreAttnFn(Function):
+    """x -> qkv = Linear_qkv(LN(x))  (self_attn_layer_norm + q/k/v projections of ONE expert, encoder.py:138-139, multihead_attention.py:91-93)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, q_w, q_b, k_w, k_b, v_w, v_b, eps):
+        qkv_w = torch.cat([q_w, k_w, v_w], dim=0)
+        qkv_b = torch.cat([q_b, k_b, v_b], dim=0)
+        h, _, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, eps)
+        qkv = ops.gemm(h, qkv_w, bias=qkv_b)
+        ctx.save_for_backward(x, mean, rstd, ln_w, ln_b, qkv_w)
+        ctx.eps = eps
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        x, mean, rstd, ln_w, ln_b, qkv_w = ctx.saved_tensors
+        W = x.shape[1]
+        dqkv = dqkv.contiguous()
+        vg = _VecGrads(x.device, [W, W, 3 * W])
+        h, _, _, _ = ops.layernorm_fwd(x, ln_w, ln_b, ctx.eps)
+        d_w = _wgrad(dqkv, h)
+        del h
+        ops.rowsum_periodic(dqkv, vg[2])
+        dh = ops.gemm(dqkv, qkv_w, b_mn=True)
+        dx = ops.layernorm_bwd(dh, x, mean, rstd, ln_w, vg[0], vg[1])
+        d_ln_w, d_ln_b, d_b = vg.finish()
+        return (dx, d_ln_w, d_ln_b, d_w[:W], d_b[:W], d_w[W: 2 * W], d_b[W: 2 * W], d_w[2 * W:], d_b[2 * W:], None)
+
+
+class AttentionFn(Function):
+    """softmax(q k^T / sqrt(hd) + key_bias) v on a fused projection buffer qkv [B*L, 3W] -> [B*L, W]."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_bias, B, L, H):
+        W = qkv.shape[1] // 3
+        o, lse = ops.attention_fwd(qkv, B, L, H, W // H, key_bias=key_bias)
+        ctx.save_for_backward(qkv, o, lse, key_bias)
+        ctx.meta = (B, L, H, W)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse, key_bias = ctx.saved_tensors
+        B, L, H, W = ctx.meta
+        return ops.attention_bwd(qkv, o, d_o.contiguous(), lse, B, L, H, W // H, key_bias=key_bias), None, None, None, None
+
+
+class XposFn(Function):
+    """Out-of-place XPOS on the q / k sections of qkv (see M2EncoderLayerFn for the in-place use inside the fused layer)."""
+
+    @staticmethod
+    def forward(ctx, qkv, tables, B, L, H):
+        ctx.tables, ctx.meta = tables, (B, L, H, qkv.shape[1] // 3 // H)
+        return ops.xpos_apply(qkv.clone(), tables, B, L, H, ctx.meta[3])
+
+    @staticmethod
+    def backward(ctx, g):
+        B, L, H, hd = ctx.meta
+        return ops.xpos_apply(g.clone().contiguous(), ctx.tables, B, L, H, hd, backward=True), None, None, None, None
+
+
+class M2PostAttnFn(Function):
+    """(a, x) -> y: inner_attn_ln, out_proj + residual, final_layer_norm, fc1, gelu + ffn_layernorm, fc2 + residual of ONE expert
+    (multihead_attention.py:148-151, encoder.py:149-167, feedforward_network.py:117-128)."""
+
+    @staticmethod
+    def forward(ctx, a, x, iln_w, iln_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fln_w, fln_b, fc2_w, fc2_b, eps):
+        a_n, _, mean_i, rstd_i = ops.layernorm_fwd(a, iln_w, iln_b, eps)
+        x_mid = ops.gemm(a_n, o_w, bias=o_b, residual=x)
+        del a_n
+        h2, _, mean2, rstd2 = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+        u = ops.gemm(h2, fc1_w, bias=fc1_b)
+        del h2
+        g_n, mean_f, rstd_f = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)
+        y = ops.gemm(g_n, fc2_w, bias=fc2_b, residual=x_mid)
+        ctx.save_for_backward(a, iln_w, iln_b, o_w, ln2_w, ln2_b, fc1_w, fln_w, fln_b, fc2_w, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (a, iln_w, iln_b, o_w, ln2_w, ln2_b, fc1_w, fln_w, fln_b, fc2_w, mean_i, rstd_i, x_mid, mean2, rstd2, u, mean_f, rstd_f) = ctx.saved_tensors
+        eps = ctx.eps
+        W, F_ = a.shape[1], fc1_w.shape[0]
+        dy = dy.contiguous()
+        vg = _VecGrads(a.device, [W, W, W, W, W, F_, F_, F_, W])  # iln w,b | o_b | ln2 w,b | fc1_b | fln w,b | fc2_b
+        g_n, _, _ = ops.act_layernorm_fwd(u, ACT_GELU_ERF, fln_w, fln_b, eps)
+        d_fc2_w = _wgrad(dy, g_n)
+        del g_n
+        ops.rowsum_periodic(dy, vg[8])
+        dg_n = ops.gemm(dy, fc2_w, b_mn=True)
+        du = ops.act_layernorm_bwd(dg_n, u, ACT_GELU_ERF, mean_f, rstd_f, fln_w, vg[6], vg[7])
+        del dg_n
+        h2, _, _, _ = ops.layernorm_fwd(x_mid, ln2_w, ln2_b, eps)
+        d_fc1_w = _wgrad(du, h2)
+        del h2
+        ops.rowsum_periodic(du, vg[5])
+        dh2 = ops.gemm(du, fc1_w, b_mn=True)
+        del du
+        dx_mid = ops.layernorm_bwd(dh2, x_mid, mean2, rstd2, ln2_w, vg[3], vg[4], dadd=dy)
+        del dh2
+        a_n, _, _, _ = ops.layernorm_fwd(a, iln_w, iln_b, eps)
+        d_o_w = _wgrad(dx_mid, a_n)
+        del a_n
+        ops.rowsum_periodic(dx_mid, vg[2])
+        da_n = ops.gemm(dx_mid, o_w, b_mn=True)
+        da = ops.layernorm_bwd(da_n, a, mean_i, rstd_i, iln_w, vg[0], vg[1])
+        d_iln_w, d_iln_b, d_o_b, d_ln2_w, d_ln2_b, d_fc1_b, d_fln_w, d_fln_b, d_fc2_b = vg.finish()
+        return (da, dx_mid, d_iln_w, d_iln_b, d_o_w, d_o_b, d_ln2_w, d_ln2_b, d_fc1_w, d_fc1_b, d_fln_w, d_fln_b, d_fc2_w, d_fc2_b, None)
+
+
+class GatherRowsFn(Function):
+    """out[r] = table[ids[r]]; backward sums the row gradients back per table row (interleaving / splitting token rows of two experts)."""
+
+    @staticmethod
+    def forward(ctx, table, ids):
+        ctx.save_for_backward(ids)
+        ctx.n = table.shape[0]
+        return ops.gather_rows(table.contiguous(), ids)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        acc = torch.zeros((ctx.n, dy.shape[1]), device=dy.device, dtype=torch.float32)
+        ops.scatter_add_rows(dy.contiguous(), ids, acc)
+        return ops.cast_f32_bf16(acc), None

@@ -14,8 +14,9 @@ The nn.Linear / nn.LayerNorm / nn.Embedding objects below are PARAMETER CONTAINE
 forward is never called — every layer runs through b200mm.functional (hand-written CUDA behind the C-ABI).
 Supported configuration = what the shipped configs use (configs/Encoder_0.4B.json, Encoder_1B.json): pre-LN + sub-LN,
 no deepnorm / MoE / relative position bias, dropout and drop-path 0, head_dim 64; XPOS (args.xpos_rel_pos, off in the shipped configs) is
-supported as an in-place rotary step on the fused QKV output. A multiway split inside one
-sequence (fused vision+language input, split_position > 0) is not on the ITC path and raises.
+supported as an in-place rotary step on the fused QKV output. A multiway split inside one sequence (fused vision+language input,
+split_position > 0; not used by the ITC path) runs the per-token parts per expert on two token matrices and attention on the joint
+sequence (`forward_tokens_mixed`).
 """
 import math
 
@@ -68,12 +69,13 @@ class MultiwayNetwork(nn.Module):
         self.split_position = -1
 
     def way(self, split_position):
+        """Expert for a whole-sequence call: -1 -> A (vision), 0 -> B (language). A split INSIDE the sequence (> 0) is handled by the
+        callers' *_mixed paths, which ask for both experts."""
         if split_position == -1:
             return self.A
         if split_position == 0:
             return self.B
-        raise NotImplementedError("b200mm M2 encoder: a multiway split inside one sequence (split_position > 0, fused vision+language "
-                                  "input) is not on the ITC path")
+        raise ValueError(f"MultiwayNetwork.way: split_position {split_position} selects no single expert")
 
 
 class FeedForwardNetwork(nn.Module):
@@ -137,6 +139,43 @@ class EncoderLayer(nn.Module):
                                          self.checkpoint, self.keep_act, self.self_attn.xpos_tables_for(L, x2d.device))
 
 
+    def _pre_post_params(self, sp):
+        a = self.self_attn
+        ln1, ln2, ffn, iln = self.self_attn_layer_norm.way(sp), self.final_layer_norm.way(sp), self.ffn.way(sp), a.inner_attn_ln.way(sp)
+        q, k, v, o = a.q_proj.way(sp), a.k_proj.way(sp), a.v_proj.way(sp), a.out_proj.way(sp)
+        pre = tuple(_bf16(t) for t in (ln1.weight, ln1.bias, q.weight, q.bias, k.weight, k.bias, v.weight, v.bias))
+        post = tuple(_bf16(t) for t in (iln.weight, iln.bias, o.weight, o.bias, ln2.weight, ln2.bias, ffn.fc1.weight, ffn.fc1.bias,
+                                        ffn.ffn_layernorm.weight, ffn.ffn_layernorm.bias, ffn.fc2.weight, ffn.fc2.bias))
+        return pre, post
+
+    def forward_tokens_mixed(self, xA, xB, idx, key_bias, B, L):
+        """Multiway split inside the sequence (multiway_network.py:38-45): rows of expert A (vision) and B (language) are kept in two
+        token matrices; only attention sees the joint [B*L] order (`idx`: merge / takeA / takeB row-id lists)."""
+        H = self.self_attn.num_heads
+        preA, postA = self._pre_post_params(-1)
+        preB, postB = self._pre_post_params(0)
+        qa = Fn.M2PreAttnFn.apply(xA, *preA, self.eps)
+        qb = Fn.M2PreAttnFn.apply(xB, *preB, self.eps)
+        qkv = Fn.GatherRowsFn.apply(torch.cat([qa, qb], dim=0), idx["merge"])
+        xp = self.self_attn.xpos_tables_for(L, qkv.device)
+        if xp is not None:
+            qkv = Fn.XposFn.apply(qkv, xp, B, L, H)
+        a = Fn.AttentionFn.apply(qkv, key_bias, B, L, H)
+        aA = Fn.GatherRowsFn.apply(a, idx["takeA"])
+        aB = Fn.GatherRowsFn.apply(a, idx["takeB"])
+        return Fn.M2PostAttnFn.apply(aA, xA, *postA, self.eps), Fn.M2PostAttnFn.apply(aB, xB, *postB, self.eps)
+
+
+def split_index(B, L, s, device):
+    """Row-id lists between the joint token order [B*L] and the two per-expert matrices A [B*s] (tokens < s) and B [B*(L-s)]."""
+    b = torch.arange(B, device=device)[:, None]
+    l = torch.arange(L, device=device)[None, :]
+    merge = torch.where(l < s, b * s + l, B * s + b * (L - s) + (l - s)).reshape(-1).contiguous()   # into cat([A, B]) rows
+    takeA = (b * L + torch.arange(s, device=device)[None, :]).reshape(-1).contiguous()
+    takeB = (b * L + s + torch.arange(L - s, device=device)[None, :]).reshape(-1).contiguous()
+    return {"merge": merge, "takeA": takeA, "takeB": takeB}
+
+
 class PositionalEmbedding(nn.Embedding):
     """component/embedding.py:93-110: positions start at 2 (fairseq convention)."""
 
@@ -189,6 +228,20 @@ class Encoder(nn.Module):
         ln = self.layer_norm.way(split_position)
         return Fn.LayerNormFn.apply(x2d, _bf16(ln.weight), _bf16(ln.bias), self.eps)
 
+    def forward_tokens_mixed(self, xA, xB, B, L, s, drop=None, key_bias=None, mask_input=True):
+        """Fused vision + language input: xA [B*s, W] (expert A rows), xB [B*(L-s), W]; drop / key_bias in the JOINT order ([B*L] / [B, L]).
+        Returns the joint [B*L, W] hidden after the per-expert final layer_norm."""
+        idx = split_index(B, L, s, xA.device)
+        if drop is not None and mask_input:
+            xA = Fn.MaskRowsFn.apply(xA, drop[idx["takeA"]].contiguous())
+            xB = Fn.MaskRowsFn.apply(xB, drop[idx["takeB"]].contiguous())
+        for layer in self.layers:
+            xA, xB = layer.forward_tokens_mixed(xA, xB, idx, key_bias, B, L)
+        lnA, lnB = self.layer_norm.way(-1), self.layer_norm.way(0)
+        xA = Fn.LayerNormFn.apply(xA, _bf16(lnA.weight), _bf16(lnA.bias), self.eps)
+        xB = Fn.LayerNormFn.apply(xB, _bf16(lnB.weight), _bf16(lnB.bias), self.eps)
+        return Fn.GatherRowsFn.apply(torch.cat([xA, xB], dim=0), idx["merge"])
+
     def forward(self, src_tokens=None, encoder_padding_mask=None, attn_mask=None, return_all_hiddens=False, token_embeddings=None,
                 multiway_split_position=None, features_only=False, incremental_state=None, positions=None, **kwargs):
         if src_tokens is not None or attn_mask is not None or incremental_state is not None or positions is not None or return_all_hiddens:
@@ -198,7 +251,12 @@ class Encoder(nn.Module):
         B, L, W = token_embeddings.shape
         sp = -1 if multiway_split_position is None else multiway_split_position
         drop, key_bias = _padding(encoder_padding_mask)
-        out = self.forward_tokens(_bf16(token_embeddings).reshape(B * L, W).contiguous(), B, L, sp, drop, key_bias)
+        x2d = _bf16(token_embeddings).reshape(B * L, W).contiguous()
+        if 0 < sp < L:
+            idx = split_index(B, L, sp, x2d.device)
+            out = self.forward_tokens_mixed(Fn.GatherRowsFn.apply(x2d, idx["takeA"]), Fn.GatherRowsFn.apply(x2d, idx["takeB"]), B, L, sp, drop, key_bias)
+        else:
+            out = self.forward_tokens(x2d, B, L, sp if sp <= 0 else 0, drop, key_bias)
         return {"encoder_out": out.view(B, L, W), "encoder_embedding": token_embeddings, "encoder_padding_mask": encoder_padding_mask,
                 "encoder_states": [], "l_aux": [None] * self.num_layers, "multiway_split_position": multiway_split_position}
 
@@ -253,20 +311,33 @@ class BEiT3(nn.Module):
             x = Fn.M2VisionEmbedFn.apply(_bf16(visual_tokens).contiguous(), _bf16(ve.proj.weight), _bf16(ve.proj.bias), _bf16(ve.cls_token),
                                          _bf16(enc.embed_positions.A.weight[2: L + 2]))
             return enc.forward_tokens(x, B, L, -1), B, L, None, None
-        if visual_tokens is not None:
-            raise NotImplementedError("b200mm BEiT3: fused vision+language input (multiway split inside the sequence) is not on the ITC path")
-        B, L = textual_tokens.shape
-        drop, key_bias = _padding(text_padding_position)
-        x = Fn.M2TextEmbedFn.apply(_bf16(self.text_embed.weight), textual_tokens, _bf16(enc.embed_positions.B.weight[2: L + 2]), drop)
-        return enc.forward_tokens(x, B, L, 0, drop, key_bias, mask_input=False), B, L, drop, key_bias
+        B, Lt = textual_tokens.shape
+        drop_t, bias_t = _padding(text_padding_position)
+        xt = Fn.M2TextEmbedFn.apply(_bf16(self.text_embed.weight), textual_tokens, _bf16(enc.embed_positions.B.weight[2: Lt + 2]), drop_t)
+        if visual_tokens is None:
+            return enc.forward_tokens(xt, B, Lt, 0, drop_t, bias_t, mask_input=False), B, Lt, drop_t, bias_t
+        # fused vision + language input (model/BEiT3.py:68-86): [vision tokens ; text tokens], split position = number of vision tokens
+        if visual_tokens.shape[0] != B:
+            raise NotImplementedError("b200mm BEiT3: fused input with repeated text (image batch a multiple of the text batch, BEiT3.py:71-74)")
+        ve = self.vision_embed
+        Lv = ve.num_position_embeddings()
+        xv = Fn.M2VisionEmbedFn.apply(_bf16(visual_tokens).contiguous(), _bf16(ve.proj.weight), _bf16(ve.proj.bias), _bf16(ve.cls_token),
+                                      _bf16(enc.embed_positions.A.weight[2: Lv + 2]))
+        L = Lv + Lt
+        drop = key_bias = None
+        if text_padding_position is not None:
+            pad = torch.cat([torch.zeros((B, Lv), dtype=torch.bool, device=textual_tokens.device), text_padding_position.to(torch.bool)], dim=1)
+            drop, key_bias = _padding(pad)
+        # the embeddings already zeroed the padded text rows (architecture/encoder.py:440); vision rows are never padded
+        return enc.forward_tokens_mixed(xv, xt, B, L, Lv, drop, key_bias, mask_input=False), B, L, drop, key_bias
 
     def forward(self, textual_tokens=None, visual_tokens=None, text_padding_position=None, attn_mask=None, vision_masked_position=None,
                 incremental_state=None, positions=None):
         if attn_mask is not None or vision_masked_position is not None or incremental_state is not None or positions is not None:
             raise NotImplementedError("b200mm BEiT3.forward: attn_mask / masked positions / incremental decoding are not on the ITC path")
         h, B, L, _, _ = self.forward_tokens(textual_tokens, visual_tokens, text_padding_position)
-        return {"encoder_out": h.view(B, L, -1), "encoder_padding_mask": text_padding_position,
-                "multiway_split_position": -1 if textual_tokens is None else 0}
+        split = -1 if textual_tokens is None else (0 if visual_tokens is None else self.vision_embed.num_position_embeddings())
+        return {"encoder_out": h.view(B, L, -1), "encoder_padding_mask": text_padding_position, "multiway_split_position": split}
 
 
 class ITCHead(nn.Module):

@@ -213,7 +213,18 @@ def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, pat
     lgv = model.logit_vl_scale.exp() * img_fv @ txt_fv.t()
     loss = 0.5 * (F.cross_entropy(lg, labels) + F.cross_entropy(lg.t(), labels)) + 0.5 * (F.cross_entropy(lgv, labels) + F.cross_entropy(lgv.t(), labels))
     loss.backward()
+    itc_grads = {n: p_.grad.detach().clone() for n, p_ in model.named_parameters() if p_.grad is not None}
+    # ---- fused vision + language input through the SAME backbone (BEiT3.forward with both modalities: multiway split inside the sequence)
+    for p_ in model.parameters():
+        p_.grad = None
+    fused = model.backbone(textual_tokens=ids, visual_tokens=image, text_padding_position=pad)
+    assert fused["multiway_split_position"] == vffn.shape[1]
+    fused_out = fused["encoder_out"]
+    Rf = torch.randn(fused_out.shape, generator=torch.Generator().manual_seed(77))
+    (fused_out * Rf * (1 - torch.cat([torch.zeros(B, vffn.shape[1], dtype=torch.long), pad], 1)).unsqueeze(-1)).sum().backward()
+    fused_grads = {n: p_.grad.detach().clone() for n, p_ in model.named_parameters() if p_.grad is not None}
     fx = {
+        "fused_hidden": fused_out.detach(), "fused_proj": Rf, "fused_grads": fused_grads,
         "config": dict(W=W, heads=heads, layers=layers, vl_layers=vl_layers, img=img, patch=patch, vocab=vocab, L=L, out_dim=out_dim,
                        xpos=xpos, max_source_positions=max_source_positions),
         "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
@@ -221,7 +232,7 @@ def make_m2(name="m2_tiny.pt", W=64, heads=2, layers=2, vl_layers=1, img=32, pat
         "image_hidden": vffn.detach(), "text_hidden": lffn.detach(),
         "img_f": img_f.detach(), "txt_f": txt_f.detach(), "img_fv": img_fv.detach(), "txt_fv": txt_fv.detach(),
         "logits": lg.detach(), "loss": loss.detach(),
-        "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None},
+        "grads": itc_grads,
     }
     torch.save(fx, os.path.join(OUT, name))
     print(name, "loss", float(loss.detach()), "params", sum(p.numel() for p in model.parameters()), "with grad", len(fx["grads"]))

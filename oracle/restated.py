@@ -452,3 +452,51 @@ def mil_nce_matrix(S, weight=None):
     both = torch.cat([S.t(), S.masked_fill(eye, float("-inf"))], dim=1)
     per_row = torch.logsumexp(both, dim=1) - torch.diagonal(S)
     return (per_row * weight).mean() if weight is not None else per_row.mean()
+
+
+def _multiway(fn, x, split):
+    """MultiwayNetwork.forward with 0 < split_position < L (vlmo/torchscale/component/multiway_network.py:38-45): expert A on the first
+    `split` tokens, expert B on the rest, concatenated along the sequence axis. fn(way, x_part) -> y_part."""
+    return torch.cat([fn("A", x[:, :split]), fn("B", x[:, split:])], dim=1)
+
+
+def m2_encoder_layer_mixed(sd, pfx, x, heads, split, key_pad=None, eps=1e-5, xpos_scale_base=None):
+    """EncoderLayer.forward (architecture/encoder.py:113-168) for a fused vision + language sequence: every per-token module is a
+    MultiwayNetwork split at `split`; attention (multihead_attention.py:66-154) runs over the joint sequence."""
+    B, L, W = x.shape
+    hd = W // heads
+    ap = pfx + "self_attn."
+    ln = lambda name: (lambda way, t: layer_norm(t, sd[f"{name}.{way}.weight"], sd[f"{name}.{way}.bias"], eps))  # noqa: E731
+    lin = lambda name: (lambda way, t: t @ sd[f"{name}.{way}.weight"].t() + sd[f"{name}.{way}.bias"])  # noqa: E731
+    h = _multiway(ln(pfx + "self_attn_layer_norm"), x, split)
+    q = (_multiway(lin(ap + "q_proj"), h, split) * hd ** -0.5).view(B, L, heads, hd).transpose(1, 2)
+    k = _multiway(lin(ap + "k_proj"), h, split).view(B, L, heads, hd).transpose(1, 2)
+    v = _multiway(lin(ap + "v_proj"), h, split).view(B, L, heads, hd).transpose(1, 2)
+    if xpos_scale_base is not None:
+        k = xpos(k.reshape(B * heads, L, hd), xpos_scale_base, downscale=True).view(B, heads, L, hd)
+        q = xpos(q.reshape(B * heads, L, hd), xpos_scale_base, downscale=False).view(B, heads, L, hd)
+    s = q @ k.transpose(-1, -2)
+    if key_pad is not None:
+        s = s.masked_fill(key_pad.bool()[:, None, None, :], float("-inf"))
+    a = (torch.softmax(s.float(), dim=-1).to(s.dtype) @ v).transpose(1, 2).reshape(B, L, W)
+    a = _multiway(ln(ap + "inner_attn_ln"), a, split)
+    x = x + _multiway(lin(ap + "out_proj"), a, split)
+    h = _multiway(ln(pfx + "final_layer_norm"), x, split)
+    return x + _multiway(lambda way, t: m2_ffn(sd, pfx + "ffn.", t, way, eps), h, split)
+
+
+def m2_fused_forward(sd, image, ids, masks, heads, xpos_scale_base=None, eps=1e-5):
+    """BEiT3.forward with both modalities (vlmo/torchscale/model/BEiT3.py:68-96) + Encoder.forward (architecture/encoder.py:388-482):
+    [vision tokens ; text tokens], split position = number of vision tokens, padding mask = [zeros ; 1 - text_masks], padded rows
+    zeroed, the layers, the final multiway layer_norm. Returns [B, Lv + Lt, W]."""
+    xv = m2_vision_embed(sd, "backbone.", image)
+    xt = m2_text_embed(sd, "backbone.", ids)
+    split = xv.shape[1]
+    x = torch.cat([xv, xt], dim=1)
+    pad = torch.cat([torch.zeros(xv.shape[:2], dtype=torch.long), 1 - masks], dim=1)
+    x = x * (1 - pad.unsqueeze(-1).to(x.dtype))
+    pfx = "backbone.encoder."
+    n_layers = 1 + max(int(k[len(pfx):].split(".")[1]) for k in sd if k.startswith(pfx + "layers."))
+    for i in range(n_layers):
+        x = m2_encoder_layer_mixed(sd, f"{pfx}layers.{i}.", x, heads, split, pad, eps, xpos_scale_base)
+    return _multiway(lambda way, t: layer_norm(t, sd[f"{pfx}layer_norm.{way}.weight"], sd[f"{pfx}layer_norm.{way}.bias"], eps), x, split)

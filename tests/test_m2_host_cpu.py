@@ -7,6 +7,7 @@ import os
 import pytest
 import torch
 
+from oracle import restated
 from tests import emulated_ops
 
 BF = torch.bfloat16
@@ -55,3 +56,52 @@ def test_m2_glue_reproduces_reference_golden(golden_dir, name, checkpoint, keep)
         n_checked += 1
         assert rel_l2(p.grad, ref) < 6e-2, (n, rel_l2(p.grad, ref))
     assert n_checked > 40
+
+
+@pytest.mark.parametrize("name", ["m2_tiny.pt", "m2_tiny_xpos.pt"])
+def test_m2_fused_input_glue_reproduces_reference_golden(golden_dir, name):
+    """Fused vision + language input (multiway split inside the sequence): two per-expert token matrices, joint attention through row
+    gathers — BEiT3.forward(textual_tokens, visual_tokens, text_padding_position) and Encoder.forward(token_embeddings, split > 0) over the
+    emulated kernels vs the golden vectors of the unmodified reference."""
+    from b200mm.modules import M2Encoder
+
+    fx = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    c = fx["config"]
+    m = M2Encoder(image_size=c["img"], patch_size=c["patch"], vocab_size=c["vocab"], encoder_embed_dim=c["W"], encoder_attention_heads=c["heads"],
+                  encoder_layers=c["layers"], beit3_vl_layers=c["vl_layers"], out_embed_dim=c["out_dim"], max_text_len=c["L"],
+                  max_source_positions=c.get("max_source_positions", 1024), xpos_rel_pos=c.get("xpos", False))
+    m.load_state_dict(fx["state_dict"], strict=False)
+    m = m.to(BF).train()
+    pad = 1 - fx["masks"]
+    Lv = fx["fused_hidden"].shape[1] - fx["ids"].shape[1]
+    valid = torch.cat([torch.ones(pad.shape[0], Lv, dtype=torch.long), fx["masks"]], 1).unsqueeze(-1)
+    with emulated_ops.patched():
+        out = m.backbone(textual_tokens=fx["ids"], visual_tokens=fx["image"].to(BF), text_padding_position=pad)
+        assert out["multiway_split_position"] == Lv
+        h = out["encoder_out"]
+        assert rel_l2(h.float() * valid, fx["fused_hidden"] * valid) < 1.5e-2, rel_l2(h.float() * valid, fx["fused_hidden"] * valid)
+        (h.float() * fx["fused_proj"] * valid).sum().backward()
+    n_checked = 0
+    for n, p in m.named_parameters():
+        ref = fx["fused_grads"].get(n)
+        if ref is None or float(ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.float().abs().max()) == 0.0, n
+            continue
+        assert p.grad is not None, n
+        if float(ref.abs().max()) < 1e-5:
+            continue
+        n_checked += 1
+        assert rel_l2(p.grad, ref) < 6e-2, (n, rel_l2(p.grad, ref))
+    assert n_checked > 40
+    # the reference's generic entry: Encoder.forward(token_embeddings=..., multiway_split_position=s) on the vl encoder
+    with emulated_ops.patched(), torch.no_grad():
+        emb = fx["fused_hidden"].to(BF)
+        full_pad = torch.cat([torch.zeros(pad.shape[0], Lv, dtype=torch.long), pad], 1)
+        mixed = m.backbone_vl(src_tokens=None, token_embeddings=emb, encoder_padding_mask=full_pad, multiway_split_position=Lv)["encoder_out"]
+        sd = {k: v.float() for k, v in fx["state_dict"].items()}
+        x = emb.float() * (1 - full_pad.unsqueeze(-1).float())
+        xp = 512 if c.get("xpos") else None
+        for i in range(c["vl_layers"]):
+            x = restated.m2_encoder_layer_mixed(sd, f"backbone_vl.layers.{i}.", x, c["heads"], Lv, full_pad, 1e-5, xp)
+        ref = restated._multiway(lambda way, t: restated.layer_norm(t, sd[f"backbone_vl.layer_norm.{way}.weight"], sd[f"backbone_vl.layer_norm.{way}.bias"], 1e-5), x, Lv)
+        assert rel_l2(mixed.float() * valid, ref * valid) < 1.5e-2

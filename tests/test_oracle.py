@@ -222,3 +222,26 @@ def test_restated_stage2_cross_similarity_and_hard_mining_match_golden(golden_di
         torch.testing.assert_close(vis.grad, h["d_vis"], rtol=1e-3, atol=1e-7)
         for n, g in h["grads"].items():
             assert float((sd[n].grad - g).abs().max() / g.abs().max().clamp_min(1e-3)) < 3e-4, (method, n)  # the last bias has an analytically zero gradient (shift invariance)
+
+
+@pytest.mark.parametrize("name", ["m2_tiny.pt", "m2_tiny_xpos.pt"])
+def test_restated_m2_fused_input_matches_golden(golden_dir, name):
+    """Multiway split INSIDE the sequence (fused vision + language input, BEiT3.forward with both modalities): restatement vs the
+    unmodified reference — joint hidden states and every parameter gradient of a fixed random projection of the valid rows."""
+    fx = _load(golden_dir, name)
+    heads = fx["config"]["heads"]
+    xp = 512 if fx["config"].get("xpos") else None
+    sd = {k: v.clone().requires_grad_(torch.is_floating_point(v)) for k, v in fx["state_dict"].items()}
+    out = restated.m2_fused_forward(sd, fx["image"], fx["ids"], fx["masks"], heads, xp)
+    torch.testing.assert_close(out, fx["fused_hidden"], rtol=1e-4, atol=3e-5)
+    Lv = out.shape[1] - fx["ids"].shape[1]
+    valid = torch.cat([torch.ones(out.shape[0], Lv, dtype=torch.long), fx["masks"]], 1).unsqueeze(-1)
+    (out * fx["fused_proj"] * valid).sum().backward()
+    assert len(fx["fused_grads"]) > 40
+    for n, g in fx["fused_grads"].items():
+        got = sd[n].grad
+        assert got is not None, n
+        assert float((got - g).abs().max() / g.abs().max().clamp_min(1e-4)) < 3e-4, n
+    # both experts of the backbone layers are exercised, the vl encoder and the heads are not
+    assert "backbone.encoder.layers.0.ffn.A.fc1.weight" in fx["fused_grads"] and "backbone.encoder.layers.0.ffn.B.fc1.weight" in fx["fused_grads"]
+    assert not any(k.startswith(("backbone_vl.", "itc_")) for k in fx["fused_grads"])
