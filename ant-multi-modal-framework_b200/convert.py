@@ -5,7 +5,8 @@ recursive `named_children()` walk + `setattr(module, name, new_module)` + `load_
 Matched by class name and structure (the reference classes are not importable from here):
   VisionTransformer  antmmf/modules/vision/backbone/clip/model.py:275-335    -> b200mm.modules.VisionTransformer
   BertModel          antmmf/modules/vision/backbone/clip/modeling_bert.py:421 -> b200mm.modules.BertModel
-  CNCLIP             antmmf/modules/vision/backbone/clip/cn_model.py:126      -> b200mm.modules.CNCLIP (adds the fused contrastive_loss)
+  BEiT3              prj/M2_Encoder/vlmo/torchscale/model/BEiT3.py:15         -> b200mm.modules.BEiT3   (multiway, sub-LN; args read from .args)
+  Encoder            prj/M2_Encoder/vlmo/torchscale/architecture/encoder.py:171 (stand-alone, e.g. VLMo.backbone_vl) -> b200mm M2 Encoder
 Parameters are copied by key (`load_state_dict`, strict), so the converted model produces the reference's results on the same inputs
 within the bf16 bars of DESIGN.md §4; everything else in the model is left untouched.
 """
@@ -38,6 +39,47 @@ def _bert_from(ref):
     return new
 
 
+def _m2_args_supported(a):
+    bad = []
+    if not getattr(a, "multiway", False):
+        bad.append("multiway=False")
+    if not getattr(a, "encoder_normalize_before", True) or not getattr(a, "subln", True) or getattr(a, "deepnorm", False):
+        bad.append("not pre-LN + sub-LN")
+    if getattr(a, "moe_freq", 0) or getattr(a, "rel_pos_buckets", 0) or getattr(a, "layernorm_embedding", False):
+        bad.append("MoE / relative position bias / embedding LayerNorm")
+    if not getattr(a, "no_output_layer", False) or getattr(a, "share_layer", False) or getattr(a, "share_attn", False):
+        bad.append("output projection / shared layers")
+    if bad:
+        raise NotImplementedError("b200mm.convert: torchscale encoder configuration not on the hot path: " + ", ".join(bad))
+
+
+def _beit3_from(ref):
+    from .modules import beit3 as B3
+
+    a = ref.args
+    _m2_args_supported(a)
+    new = B3.BEiT3(img_size=a.img_size, patch_size=a.patch_size, in_chans=a.in_chans, vocab_size=a.vocab_size,
+                   encoder_embed_dim=a.encoder_embed_dim, encoder_attention_heads=a.encoder_attention_heads,
+                   encoder_ffn_embed_dim=a.encoder_ffn_embed_dim, encoder_layers=len(ref.encoder.layers),
+                   max_source_positions=a.max_source_positions, layernorm_eps=a.layernorm_eps, xpos_rel_pos=a.xpos_rel_pos,
+                   xpos_scale_base=a.xpos_scale_base)
+    new.load_state_dict(ref.state_dict())
+    return new
+
+
+def _m2_encoder_from(ref):
+    from .modules import beit3 as B3
+
+    a = ref.args
+    _m2_args_supported(a)
+    if ref.embed_positions is not None or ref.embed_tokens is not None:
+        raise NotImplementedError("b200mm.convert: a torchscale Encoder with its own embeddings is converted through its BEiT3 owner")
+    new = B3.Encoder(a.encoder_embed_dim, a.encoder_attention_heads, a.encoder_ffn_embed_dim, len(ref.layers), a.layernorm_eps,
+                     xpos_rel_pos=a.xpos_rel_pos, xpos_scale_base=a.xpos_scale_base)
+    new.load_state_dict(ref.state_dict())
+    return new
+
+
 def _is_ref(module, name):
     return type(module).__name__ == name and not type(module).__module__.startswith("b200mm")
 
@@ -47,6 +89,10 @@ def _convert_one(child):
         return _vit_from(child)
     if _is_ref(child, "BertModel") and hasattr(child, "embeddings") and hasattr(child, "encoder") and hasattr(child, "config"):
         return _bert_from(child)
+    if _is_ref(child, "BEiT3") and hasattr(child, "vision_embed") and hasattr(child, "text_embed") and hasattr(child, "args"):
+        return _beit3_from(child)
+    if _is_ref(child, "Encoder") and hasattr(child, "layers") and hasattr(child, "args") and hasattr(child, "embed_positions"):
+        return _m2_encoder_from(child)
     return None
 
 

@@ -54,3 +54,58 @@ def test_convert_leaves_foreign_models_alone():
 
     m = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.LayerNorm(4))
     assert b200mm.convert(m) is m and m._b200mm_converted == []
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs the reference tree")
+@pytest.mark.parametrize("xpos", [False, True])
+def test_convert_swaps_reference_beit3_and_vl_encoder(xpos):
+    """The M²-Encoder family: an unmodified reference BEiT3 + stand-alone torchscale Encoder (VLMo.backbone / backbone_vl) inside a
+    holder module are swapped in place; the converted modules keep the reference's keyword interface, so the lines of
+    VLMo.infer_image / infer_text (vlmo_module.py:333-343,385-391) run unchanged on them and reproduce the reference's hiddens."""
+    import copy
+
+    import b200mm
+
+    m2 = ref_loader.load_m2()
+    torch.manual_seed(0)
+    args = m2.EncoderConfig(img_size=32, patch_size=8, vocab_size=128, multiway=True, layernorm_embedding=False, normalize_output=True,
+                            no_output_layer=True, encoder_embed_dim=64, encoder_attention_heads=2, encoder_layers=2, encoder_ffn_embed_dim=256,
+                            checkpoint_activations=False, max_text_len=10, max_source_positions=24, xpos_rel_pos=xpos)
+    holder = torch.nn.Module()
+    holder.backbone = m2.BEiT3(args)
+    vl = copy.copy(args)
+    vl.encoder_layers = 1
+    holder.backbone_vl = m2.Encoder(vl)
+    holder.eval()
+    g = torch.Generator().manual_seed(5)
+    image = torch.randn(3, 3, 32, 32, generator=g)
+    ids = torch.randint(1, 128, (3, 10), generator=g)
+    pad = torch.zeros(3, 10, dtype=torch.long)
+    pad[1, 7:] = 1
+    with torch.no_grad():
+        r_img = holder.backbone(visual_tokens=image)["encoder_out"]
+        r_txt = holder.backbone(textual_tokens=ids, text_padding_position=pad)["encoder_out"]
+        r_vl = holder.backbone_vl(src_tokens=None, token_embeddings=r_txt, encoder_padding_mask=pad, multiway_split_position=-1)["encoder_out"]
+    keys = set(holder.state_dict())
+    b200mm.convert(holder)
+    assert sorted(holder._b200mm_converted) == ["backbone", "backbone_vl"] and set(holder.state_dict()) == keys
+    assert type(holder.backbone).__module__.startswith("b200mm") and type(holder.backbone_vl).__module__.startswith("b200mm")
+    valid = (pad == 0).unsqueeze(-1)
+    with emulated_ops.patched(), torch.no_grad():
+        img = holder.backbone(visual_tokens=image.to(BF))["encoder_out"]
+        txt = holder.backbone(textual_tokens=ids, text_padding_position=pad)["encoder_out"]
+        out_vl = holder.backbone_vl(src_tokens=None, token_embeddings=txt, encoder_padding_mask=pad, multiway_split_position=-1)["encoder_out"]
+    assert rel_l2(img, r_img) < 1.5e-2
+    assert rel_l2(txt.float() * valid, r_txt * valid) < 1.5e-2
+    assert rel_l2(out_vl.float() * valid, r_vl * valid) < 2e-2
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs the reference tree")
+def test_convert_rejects_torchscale_configurations_off_the_path():
+    import b200mm
+
+    m2 = ref_loader.load_m2()
+    args = m2.EncoderConfig(img_size=32, patch_size=8, vocab_size=64, multiway=True, no_output_layer=True, encoder_embed_dim=64,
+                            encoder_attention_heads=2, encoder_layers=1, encoder_ffn_embed_dim=128, deepnorm=True)
+    with pytest.raises(NotImplementedError, match="sub-LN"):
+        b200mm.convert(m2.BEiT3(args))
