@@ -117,3 +117,66 @@ class _ScaledSimFn(torch.autograd.Function):
         d_txt = ops.gemm(gp, img, a_mn=True, b_mn=True, alpha=alpha)[:Bt]
         d_ls = (g.float() * logits).sum().to(sdt)
         return d_img, d_txt.contiguous(), d_ls
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# module-level loader API of cn_model.py:229-420 (build_model / load / available_models, the two single-tower wrappers)
+# ----------------------------------------------------------------------------------------------------------------------
+def available_models():
+    """Names of the CN-CLIP sizes this path builds (cn_model.py:352-354; the RN50 tower is not on the path)."""
+    return list(CONFIGS.keys())
+
+
+def build_model(config: dict, state_dict: dict = None):
+    """cn_model.py:308-316: CNCLIP(**config), parameters copied by key (a leading `module.` of DDP checkpoints is dropped), eval mode."""
+    model = CNCLIP(**config)
+    if state_dict is not None:
+        own = model.state_dict()
+        clean = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        missing = [k for k in own if k not in clean]
+        if missing:
+            raise KeyError(f"b200mm build_model: checkpoint lacks {len(missing)} parameters, e.g. {missing[:3]}")
+        for k in own:
+            own[k].copy_(clean[k])
+    return model.eval()
+
+
+def load(name: str, config: dict = None, pretrained: bool = True, device="cpu", download_root: str = None):
+    """cn_model.py:357-409 without the download step (there is no network on this path): `name` is a size from CONFIGS (with
+    pretrained=False) or the path of a CN-CLIP checkpoint file ({"state_dict": ...}); `config` defaults to CONFIGS[name]."""
+    import os
+
+    if config is None:
+        if name not in CONFIGS:
+            raise RuntimeError(f"Model {name} not found; available models = {available_models()} (or pass `config` with a checkpoint path)")
+        config = CONFIGS[name]
+    if not pretrained:
+        return build_model(config).to(device)
+    if not os.path.isfile(name):
+        raise RuntimeError(f"b200mm load: pretrained=True needs a local checkpoint path, got {name!r} (downloads are not supported); "
+                           f"available sizes = {available_models()}")
+    ckpt = torch.load(name, map_location="cpu")
+    state_dict = ckpt["state_dict"] if isinstance(ckpt, dict) and "state_dict" in ckpt else ckpt
+    return build_model(config, state_dict).to(device)
+
+
+class CNCLIPImageEncoder(nn.Module):
+    """cn_model.py:229-250: `forward(x) = model.encode_image(x)`."""
+
+    def __init__(self, model_name, config=None, pretrained=True):
+        super().__init__()
+        self.model = load(model_name, config, pretrained)
+
+    def forward(self, x):
+        return self.model.encode_image(x)
+
+
+class CNCLIPLanguageEncoder(nn.Module):
+    """cn_model.py:253-273: `forward(text) = model.encode_text(text)`."""
+
+    def __init__(self, model_name, config=None, pretrained=True):
+        super().__init__()
+        self.model = load(model_name, config, pretrained)
+
+    def forward(self, text):
+        return self.model.encode_text(text)

@@ -120,3 +120,29 @@ def test_m2_encoder_state_dict_keys_match_reference(golden_dir, name):
                                 max_source_positions=c.get("max_source_positions", 1024))
         live = {"backbone." + k: tuple(v.shape) for k, v in m2.BEiT3(args).state_dict().items()}
         assert all(ours[k] == s for k, s in live.items())
+
+
+def test_cnclip_loader_api(tmp_path, golden_dir):
+    """build_model / load / available_models and the single-tower wrappers of cn_model.py:229-420 (no download step)."""
+    from b200mm.modules import CNCLIPImageEncoder, CNCLIPLanguageEncoder, available_models, build_model, load
+
+    assert available_models() == ["ViT-B-16", "ViT-L-14", "ViT-L-14-336", "ViT-H-14"]
+    fx = torch.load(os.path.join(golden_dir, "cnclip_tiny.pt"), weights_only=False)
+    ckpt = tmp_path / "tiny.pt"
+    torch.save({"state_dict": {"module." + k: v for k, v in fx["state_dict"].items()}}, ckpt)  # a DDP-style checkpoint
+    m = load(str(ckpt), fx["config"], pretrained=True)
+    assert not m.training
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, fx["state_dict"][k]), k
+    assert isinstance(CNCLIPImageEncoder(str(ckpt), fx["config"]).model, type(m))
+    assert isinstance(CNCLIPLanguageEncoder(str(ckpt), fx["config"]).model, type(m))
+    fresh = build_model(fx["config"])
+    assert set(fresh.state_dict()) == set(fx["state_dict"])
+    with pytest.raises(RuntimeError, match="local checkpoint path"):
+        load("ViT-B-16", pretrained=True)
+    with pytest.raises(RuntimeError, match="not found"):
+        load("RN50", pretrained=False)
+    bad = dict(fx["state_dict"])
+    bad.pop("logit_scale")
+    with pytest.raises(KeyError):
+        build_model(fx["config"], bad)
