@@ -50,3 +50,23 @@ def test_cnclip_glue_reproduces_reference_golden(golden_dir, name, policy):
         checked += 1
     assert checked > 40
     assert float(m.bert.embeddings.word_embeddings.weight.grad[0].abs().max()) == 0.0  # padding_idx row
+
+
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.float16])
+def test_modules_accept_fp32_fp16_inputs_under_autocast(golden_dir, in_dtype):
+    """Trainer coupling (SURVEY.md §8b iv): the unmodified trainer may call the model under fp16 autocast with fp32 / fp16 inputs and fp32
+    master parameters (base_trainer.py:334-349); the modules cast at their boundary and give the same features as the bf16 call."""
+    from b200mm.modules import CNCLIP
+
+    fx = torch.load(os.path.join(golden_dir, "cnclip_tiny.pt"), weights_only=False)
+    m = CNCLIP(**fx["config"])
+    m.load_state_dict(fx["state_dict"])
+    m.train()  # fp32 master parameters: cast to bf16 per call
+    with emulated_ops.patched():
+        ref_img, ref_txt = m.to(BF).encode_normalized(fx["image"].to(BF), fx["text"])
+        m = m.float()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            img, txt = m.encode_normalized(fx["image"].to(in_dtype), fx["text"])
+    assert img.dtype == BF and txt.dtype == BF
+    assert rel_l2(img, ref_img) < 1e-2 and rel_l2(txt, ref_txt) < 1e-2
+    assert rel_l2(img, fx["image_features"]) < 2e-2
