@@ -19,6 +19,8 @@
 // BERT q/k/v GEMM): head h of q at column q_off + h*hd, k at k_off + h*hd, v at v_off + h*hd. O is [B, L, ldo].
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace b200mm {
@@ -482,6 +484,12 @@ static int dispatch_attn(int which, int hd, const AttnParams& p, cudaStream_t st
   }
 }
 
+int attention_fwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
+                     const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, cudaStream_t stream);
+int attention_bwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o, int64_t ldo,
+                     const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H, int32_t L, int32_t head_dim,
+                     float scale, cudaStream_t stream);
+
 static int check_common(const char* who, const void* qkv, int64_t ld, const void* o, int64_t ldo, int32_t B, int32_t H, int32_t L,
                         int32_t hd, int32_t q_off, int32_t k_off, int32_t v_off) {
   B200MM_REQUIRE(B > 0 && H > 0 && L > 0, B200MM_ERR_SHAPE, "%s: B=%d H=%d L=%d", who, B, H, L);
@@ -503,6 +511,8 @@ extern "C" int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, 
   int rc = check_common("attention_fwd", qkv, ld, o, ldo, B, H, L, head_dim, q_off, k_off, v_off);
   if (rc) return rc;
   B200MM_REQUIRE(lse != nullptr, B200MM_ERR_SHAPE, "attention_fwd: lse is required");
+  if (!getenv("B200MM_ATTN_OLD"))
+    return attention_fwd_v3(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, reinterpret_cast<cudaStream_t>(stream));
   rc = attention_fwd_tc(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B200MM_OK;
   AttnParams p{};
@@ -520,6 +530,9 @@ extern "C" int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, 
   B200MM_REQUIRE(lse && d_o && dqkv && dsum, B200MM_ERR_SHAPE, "attention_bwd: null pointer");
   B200MM_REQUIRE((reinterpret_cast<uintptr_t>(d_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, B200MM_ERR_ALIGN,
                  "attention_bwd: d_o/dqkv must be 16B aligned");
+  if (!getenv("B200MM_ATTN_OLD"))
+    return attention_bwd_v3(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale,
+                            reinterpret_cast<cudaStream_t>(stream));
   rc = attention_bwd_tc(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale,
                         reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B200MM_OK;
