@@ -53,25 +53,28 @@ __device__ __forceinline__ float a3_fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// Every mbarrier wait of these kernels goes through here. With A3_WATCHDOG a wait that outlives any legitimate latency (seconds)
-// reports which barrier / role / parity it was and traps, so that a protocol bug surfaces as a CUDA error instead of a hung GPU.
+// Every mbarrier wait of these kernels goes through here. A wait that outlives any legitimate latency (seconds) traps, so that a protocol
+// bug surfaces as a CUDA error instead of a hung GPU; build with -DA3_WATCHDOG=2 to also print which barrier / role / parity it was
+// (the printf costs a stack frame and ~25 % of the kernel time, bring-up only), -DA3_WATCHDOG=0 removes the counter.
 #ifndef A3_WATCHDOG
-#define A3_WATCHDOG 0
+#define A3_WATCHDOG 1
 #endif
 __device__ __forceinline__ void a3_wait(uint64_t* bar, uint32_t parity, int tag) {
 #if A3_WATCHDOG
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins == (1u << 24)) {
+#if A3_WATCHDOG > 1
       printf("b200mm attention: mbarrier wait timed out (tag %d, parity %u, block %d, thread %d)\n", tag, parity, blockIdx.x, threadIdx.x);
+#endif
       __trap();
     }
   }
 #else
-  (void)tag;
   while (!mbar_try_wait(bar, parity)) {
   }
 #endif
+  (void)tag;
 }
 // ex2 whose position in the instruction stream is pinned (volatile): the softmax loops issue a whole 16-column chunk of MUFU ops back to
 // back and only then consume the PREVIOUS chunk, so the ~40-cycle MUFU latency (measured, tools/ubench) is never exposed. Left to itself
@@ -304,57 +307,80 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       int it1 = 0, tk1 = 0;
       uint32_t upar = 0;   // (g >> 1) & 1 of the current pair
       uint32_t cpar0 = 0;  // parity of (u * n_blk) for the current pair
-      auto issue_s = [&](int x, int j) {
-        if (j == 0) a3_wait(&q_full[x], upar, 2 /*q_full*/);
-        int st;
-        uint32_t par;
-        bool last = true;
+      // ring cursor of the next K / V block of slot x (resident: derived from the unit; streamed: the running ring position)
+      auto k_pos = [&](int x, int j, int& st, uint32_t& par, bool& last) {
         if (p.resident) {
           st = ((x ? it1 : it) & 1) * p.n_blk + j;
           par = ((x ? it1 : it) >> 1) & 1;
           last = (x ? tk1 : tk) == p.n_qt - 1;
         } else {
-          st = ks; par = kpar;
+          st = ks; par = kpar; last = true;
           if (++ks == p.NS) { ks = 0; kpar ^= 1; }
         }
-        a3_wait(&k_full[st], par, 3 /*k_full*/);
-        tc_fence_after();
+      };
+      auto v_pos = [&](int x, int j, int& st, uint32_t& par, bool& last) {
+        if (p.resident) {
+          st = ((x ? it1 : it) & 1) * p.n_blk + j;
+          par = ((x ? it1 : it) >> 1) & 1;
+          last = (x ? tk1 : tk) == p.n_qt - 1;
+        } else {
+          st = vs; par = vpar; last = true;
+          if (++vs == p.NS) { vs = 0; vpar ^= 1; }
+        }
+      };
+      // S(x, 0): first block of a unit
+      auto issue_s0 = [&](int x) {
+        int st;
+        uint32_t par;
+        bool last;
+        k_pos(x, 0, st, par, last);
         const uint64_t qd = qd0 + x * qslot16, kd = kd0 + st * stage16;
-        const uint32_t idesc = j == p.n_blk - 1 ? idesc_s_last : idesc_s_full;
+        const uint32_t idesc = p.n_blk == 1 ? idesc_s_last : idesc_s_full;
         const uint32_t td = tmem_base + x * 128;
+        a3_wait(&k_full[st], par, 3 /*k_full*/);
+        a3_wait(&q_full[x], upar, 2 /*q_full*/);
+        tc_fence_after();
         if (a3_elect_one()) {
           for (int k4 = 0; k4 < ksteps; ++k4)
             umma_bf16(td, qd + (k4 >> 2) * 1024 + (k4 & 3) * 2, kd + (k4 >> 2) * slab16 + (k4 & 3) * 2, idesc, k4 > 0);
           umma_commit(&s_full[x]);
           if (last) umma_commit(&k_empty[st]);
-          if (j == p.n_blk - 1) umma_commit(&q_empty[x]);
+          if (p.n_blk == 1) umma_commit(&q_empty[x]);
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int x, int j) {
-        a3_wait(&p_full[x], (cpar0 + j) & 1, 4 /*p_full*/);
-        int st;
-        uint32_t par;
-        bool last = true;
-        if (p.resident) {
-          st = ((x ? it1 : it) & 1) * p.n_blk + j;
-          par = ((x ? it1 : it) >> 1) & 1;
-          last = (x ? tk1 : tk) == p.n_qt - 1;
-        } else {
-          st = vs; par = vpar;
-          if (++vs == p.NS) { vs = 0; vpar ^= 1; }
-        }
-        a3_wait(&v_full[st], par, 5 /*v_full*/);
-        if (j == 0) a3_wait(&o_empty[x], upar ^ 1, 6 /*o_empty*/);
-        tc_fence_after();
+      // PV(x, j) followed by S(x, j+1). Everything that does not depend on the softmax (operand barriers, descriptors) is settled BEFORE
+      // the wait on P: each mbarrier test costs ~90 cycles even when it succeeds, and the softmax group of this slot sits idle from its
+      // arrival on p_full until S(j+1) lands.
+      auto issue_pv_s = [&](int x, int j) {
+        int vst, kst = 0;
+        uint32_t vpr, kpr = 0;
+        bool vlast, klast = false;
+        v_pos(x, j, vst, vpr, vlast);
+        const bool more = j + 1 < p.n_blk;
+        if (more) k_pos(x, j + 1, kst, kpr, klast);
         const int nk = (j == p.n_blk - 1 ? p.kb_last : p.KB) >> 4;
-        const uint64_t vd = vd0 + st * stage16;
-        const uint32_t td = tmem_base + 256 + x * 128, ta = tmem_base + x * 128;
+        const uint64_t vd = vd0 + vst * stage16;
+        const uint32_t to = tmem_base + 256 + x * 128, ts = tmem_base + x * 128;
+        const uint64_t qd = qd0 + x * qslot16, kd = kd0 + kst * stage16;
+        const uint32_t idesc = j + 1 == p.n_blk - 1 ? idesc_s_last : idesc_s_full;
+        a3_wait(&v_full[vst], vpr, 5 /*v_full*/);
+        if (j == 0) a3_wait(&o_empty[x], upar ^ 1, 6 /*o_empty*/);
+        if (more) a3_wait(&k_full[kst], kpr, 3 /*k_full*/);
+        a3_wait(&p_full[x], (cpar0 + j) & 1, 4 /*p_full*/);
+        tc_fence_after();
         if (a3_elect_one()) {
-          for (int kk = 0; kk < nk; ++kk) a3_umma_ts(td, ta + kk * 8, vd + kk * 128, idesc_pv, (j > 0 || kk > 0));
+          for (int kk = 0; kk < nk; ++kk) a3_umma_ts(to, ts + kk * 8, vd + kk * 128, idesc_pv, (j > 0 || kk > 0));
           umma_commit(&pv_done[x]);
-          if (last) umma_commit(&v_empty[st]);
-          if (j == p.n_blk - 1) umma_commit(&o_full[x]);
+          if (vlast) umma_commit(&v_empty[vst]);
+          if (!more) umma_commit(&o_full[x]);
+          if (more) {
+            for (int k4 = 0; k4 < ksteps; ++k4)
+              umma_bf16(ts, qd + (k4 >> 2) * 1024 + (k4 & 3) * 2, kd + (k4 >> 2) * slab16 + (k4 & 3) * 2, idesc, k4 > 0);
+            umma_commit(&s_full[x]);
+            if (klast) umma_commit(&k_empty[kst]);
+            if (j + 1 == p.n_blk - 1) umma_commit(&q_empty[x]);
+          }
         }
         __syncwarp();
       };
@@ -362,12 +388,9 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int n_u = G - g0 < 2 ? G - g0 : 2;
         tk1 = tk + 1 == p.n_qt ? 0 : tk + 1;
         it1 = tk + 1 == p.n_qt ? it + 1 : it;
-        for (int x = 0; x < n_u; ++x) issue_s(x, 0);
+        for (int x = 0; x < n_u; ++x) issue_s0(x);
         for (int j = 0; j < p.n_blk; ++j)
-          for (int x = 0; x < n_u; ++x) {
-            issue_pv(x, j);
-            if (j + 1 < p.n_blk) issue_s(x, j + 1);
-          }
+          for (int x = 0; x < n_u; ++x) issue_pv_s(x, j);
         for (int x = 0; x < 2; ++x)
           if (++tk == p.n_qt) { tk = 0; ++it; }
         upar ^= 1;
@@ -752,39 +775,51 @@ attn3_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
       if (p.resident) { st = (c.it & 1) * p.n_in + c.i; par = (c.it >> 1) & 1; }
       else { st = c.ys; par = c.ypar; }
     };
-    auto issue_t = [&](int f) {
-      const int t = f & 1, xs = ct.g & 1;
-      if (ct.i == 0) a3_wait(&x_full[xs], (ct.g >> 1) & 1, 11 /*x_full*/);
-      int st;
+    // T(f): S / dP of flat step f (cursor ct)
+    auto t_waits = [&](int& st) {
       uint32_t par;
       stage_of(ct, st, par);
+      if (ct.i == 0) a3_wait(&x_full[ct.g & 1], (ct.g >> 1) & 1, 11 /*x_full*/);
       a3_wait(&y_full[st], par, 12 /*y_full*/);
-      tc_fence_after();
+    };
+    auto t_issue = [&](int f, int st) {  // inside an elected region
+      const int t = f & 1, xs = ct.g & 1;
       const uint32_t idesc = ct.i == p.n_in - 1 ? idesc_t_last : idesc_t_full;
       const uint64_t xd = xd0 + xs * 2 * xtile16, yd = yd0 + st * stage16;
       const uint32_t t0 = tmem_base + 2 * t * p.NB, t1 = t0 + p.NB;
-      if (a3_elect_one()) {
-        for (int k4 = 0; k4 < ksteps; ++k4) {
-          const int ao = (k4 >> 2) * 1024 + (k4 & 3) * 2, bo = (k4 >> 2) * yslab16 + (k4 & 3) * 2;
-          umma_bf16(t0, xd + ao, yd + bo, idesc, k4 > 0);
-          umma_bf16(t1, xd + xtile16 + ao, yd + ytile16 + bo, idesc, k4 > 0);
-        }
-        umma_commit(&sd_full[t]);
+      for (int k4 = 0; k4 < ksteps; ++k4) {
+        const int ao = (k4 >> 2) * 1024 + (k4 & 3) * 2, bo = (k4 >> 2) * yslab16 + (k4 & 3) * 2;
+        umma_bf16(t0, xd + ao, yd + bo, idesc, k4 > 0);
+        umma_bf16(t1, xd + xtile16 + ao, yd + ytile16 + bo, idesc, k4 > 0);
       }
+      umma_commit(&sd_full[t]);
+    };
+    auto issue_t = [&](int f) {
+      int st;
+      t_waits(st);
+      tc_fence_after();
+      if (a3_elect_one()) t_issue(f, st);
       __syncwarp();
       advance(ct);
     };
-    auto issue_acc = [&](int f) {
+    // acc(f) followed by T(f+2). The operand barriers of T(f+2) are settled before the wait on the elementwise warps when that cannot
+    // deadlock (its ring stage is not the one acc(f) is about to release): every mbarrier test costs ~90 cycles, and the elementwise warps
+    // of this stage idle until T(f+2) lands.
+    // (with one block per unit T(f+2) belongs to the unit after next, whose operand slot is only released by acc(f) itself)
+    const bool prewait = p.n_in >= 2 && (p.resident || p.NS >= 3);
+    auto issue_acc_t = [&](int f) {
       const int t = f & 1, xs = ca.g & 1;
-      a3_wait(&pds_full[t], (f >> 1) & 1, 13 /*pds_full*/);
-      if (ca.i == 0) a3_wait(&acc_empty, (ca.g & 1) ^ 1, 14 /*acc_empty*/);  // the previous unit's accumulators have been read out
-      int st;
+      const bool has_t = f + 2 < F;
+      int st, tst = 0;
       uint32_t par;
       stage_of(ca, st, par);
-      tc_fence_after();
       const int n_ch = (ca.i == p.n_in - 1 ? p.nb_last : p.NB) >> 4;
       const uint64_t yd = ymn0 + st * stage16;
       const uint32_t t0 = tmem_base + 2 * t * p.NB, t1 = t0 + p.NB;
+      if (has_t && prewait) t_waits(tst);
+      if (ca.i == 0) a3_wait(&acc_empty, (ca.g & 1) ^ 1, 14 /*acc_empty*/);  // the previous unit's accumulators have been read out
+      a3_wait(&pds_full[t], (f >> 1) & 1, 13 /*pds_full*/);
+      tc_fence_after();
       if (a3_elect_one()) {
         for (int wi = 0; wi < 3; ++wi) {
           const int c0 = (wi * n_ch) / 3, c1 = ((wi + 1) * n_ch) / 3;
@@ -800,16 +835,16 @@ attn3_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
           umma_commit(&acc_full);
           umma_commit(&x_empty[xs]);
         }
+        if (has_t && prewait) t_issue(f + 2, tst);
       }
       __syncwarp();
       advance(ca);
+      if (has_t && prewait) advance(ct);
+      if (has_t && !prewait) issue_t(f + 2);
     };
     if (F > 0) issue_t(0);
     if (F > 1) issue_t(1);
-    for (int f = 0; f < F; ++f) {
-      issue_acc(f);
-      if (f + 2 < F) issue_t(f + 2);
-    }
+    for (int f = 0; f < F; ++f) issue_acc_t(f);
   } else if (warp >= 4) {
     // ===================== elementwise + epilogue: 3 warps per lane quarter, each owns a column range of the block =====================
     const int quarter = warp & 3, wi = (warp >> 2) - 1;
@@ -1179,6 +1214,10 @@ static int a3_launch_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_o
   return check_launch(MODE == A3_MODE_DKV ? "attn3_bwd_kernel<dkv>" : "attn3_bwd_kernel<dq>");
 }
 
+int attention_bwd_merged(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* d_o, int64_t ldo,
+                         const float* lse, const float* key_bias, void* dqkv, const float* dsum, int32_t B, int32_t H, int32_t L, int32_t head_dim,
+                         float scale, cudaStream_t stream);  // attention_tc.cu
+
 int attention_bwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o, int64_t ldo,
                      const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H, int32_t L, int32_t head_dim,
                      float scale, cudaStream_t stream) {
@@ -1190,9 +1229,50 @@ int attention_bwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
                                                                                     head_dim);
   int rc = check_launch("attn3_dsum_kernel");
   if (rc) return rc;
+  // head_dim 64 and <= 288 tokens: dQ, dK and dV of an item fit the 512 TMEM columns together -> one merged kernel, 5 GEMMs and one exp
+  // per score instead of the 7 + 2 of the recompute pair (attention_tc.cu)
+  rc = attention_bwd_merged(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale, stream);
+  if (rc != 0) return rc < 0 ? rc : B200MM_OK;
   rc = a3_launch_bwd<A3_MODE_DKV>(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, dsum, key_bias, dqkv, B, H, L, head_dim, scale, stream);
   if (rc) return rc;
   return a3_launch_bwd<A3_MODE_DQ>(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, dsum, key_bias, dqkv, B, H, L, head_dim, scale, stream);
 }
 
 }  // namespace b200mm
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C-ABI (include/b200mm.h)
+// ---------------------------------------------------------------------------------------------------------------------
+using namespace b200mm;
+
+static int attn_check_common(const char* who, const void* qkv, int64_t ld, const void* o, int64_t ldo, int32_t B, int32_t H, int32_t L, int32_t hd,
+                             int32_t q_off, int32_t k_off, int32_t v_off) {
+  B200MM_REQUIRE(B > 0 && H > 0 && L > 0, B200MM_ERR_SHAPE, "%s: B=%d H=%d L=%d", who, B, H, L);
+  B200MM_REQUIRE(static_cast<int64_t>(B) * H < (1ll << 31) && static_cast<int64_t>(B) * L < (1ll << 31), B200MM_ERR_SHAPE,
+                 "%s: B*H or B*L too large", who);
+  B200MM_REQUIRE(qkv && o, B200MM_ERR_SHAPE, "%s: null pointer", who);
+  B200MM_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && hd % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0,
+                 B200MM_ERR_ALIGN, "%s: pitches/offsets must be multiples of 8 elements and bases 16B aligned", who);
+  return B200MM_OK;
+}
+
+extern "C" int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
+                                    const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, void* stream) {
+  int rc = attn_check_common("attention_fwd", qkv, ld, o, ldo, B, H, L, head_dim, q_off, k_off, v_off);
+  if (rc) return rc;
+  B200MM_REQUIRE(lse != nullptr, B200MM_ERR_SHAPE, "attention_fwd: lse is required");
+  return attention_fwd_v3(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o,
+                                    int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H,
+                                    int32_t L, int32_t head_dim, float scale, void* stream) {
+  int rc = attn_check_common("attention_bwd", qkv, ld, o, ldo, B, H, L, head_dim, q_off, k_off, v_off);
+  if (rc) return rc;
+  B200MM_REQUIRE(lse && d_o && dqkv && dsum, B200MM_ERR_SHAPE, "attention_bwd: null pointer");
+  B200MM_REQUIRE((reinterpret_cast<uintptr_t>(d_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, B200MM_ERR_ALIGN,
+                 "attention_bwd: d_o/dqkv must be 16B aligned");
+  return attention_bwd_v3(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale,
+                          reinterpret_cast<cudaStream_t>(stream));
+}

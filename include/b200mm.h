@@ -109,7 +109,8 @@ int b200mm_embed_layernorm_fwd(const void* word, const int64_t* ids, const void*
  *   ViT : nn.MultiheadAttention in ResidualAttentionBlock.attention, clip/model.py:245-251
  *   BERT: BertSelfAttention.forward, clip/modeling_bert.py:134-172 (key_bias = (1-mask)*-10000, f32 [B, L])
  * qkv: bf16 [B, L, ld]; head h of q/k/v at column {q,k,v}_off + h*head_dim.  o: bf16 [B, L, ldo] (head h at h*head_dim).
- * lse: f32 [B, H, L] (natural log).  head_dim in {32, 64, 80}.  scale = 1/sqrt(head_dim).
+ * lse: f32 [B, H, L] (natural log).  head_dim: any multiple of 16 up to 128; any L.  scale = 1/sqrt(head_dim).
+ * M2-Encoder: MultiheadAttention.forward, prj/M2_Encoder/vlmo/torchscale/component/multihead_attention.py:85-150 (head_dim 64 / 128).
  * bwd writes dq/dk/dv into dqkv (same layout as qkv) and D = rowsum(dO*O) into dsum f32 [B, H, L].
  * ------------------------------------------------------------------------------------------- */
 int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,

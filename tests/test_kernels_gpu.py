@@ -156,10 +156,13 @@ def test_embed_layernorm_bit_exact_indexing(ops):
 @pytest.mark.parametrize("B,L,H,hd,masked", [(3, 5, 2, 32, False), (2, 77, 3, 64, True), (2, 257, 2, 64, False), (2, 50, 2, 80, True),
                                              (1, 577, 1, 80, False), (2, 86, 12, 64, True), (2, 12, 2, 16, True),
                                              (3, 197, 2, 64, False), (2, 288, 2, 64, True), (2, 300, 1, 64, False), (1, 128, 1, 64, False),
-                                             (150, 257, 2, 64, False)])
+                                             (150, 257, 2, 64, False), (2, 577, 2, 64, False), (2, 200, 2, 128, False),
+                                             (3, 160, 4, 96, True), (1, 1000, 2, 64, True), (40, 86, 12, 64, True)])
 def test_attention_fwd_bwd(ops, B, L, H, hd, masked):
-    """hd == 64 and L <= 288 run the tcgen05 kernels (attention_tc.cu); other shapes the legacy mma.sync kernels. The last case
-    has more (batch, head) items than SMs, so the persistent kernels loop and recycle their mbarrier phases."""
+    """Every shape runs on the tcgen05 kernels (attention_v3.cu; backward of head_dim 64 with <= 288 tokens on the merged kernel of
+    attention_tc.cu, everything else on the recompute pair): head_dim 16..128, one to eight key blocks, resident and streamed K/V, short
+    last tiles. (150, 257, 2, 64) and (40, 86, 12, 64) have more (batch, head) items than SMs, so the persistent kernels loop and recycle
+    their mbarrier phases and operand rings."""
     W = H * hd
     qkv = rnd(B * L, 3 * W, scale=1.0, seed=B * L + hd)
     d_o = rnd(B * L, W, seed=7)

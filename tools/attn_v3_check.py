@@ -86,9 +86,7 @@ def timing():
               (64, 249, 32, 128, False)]
     for B, L, H, hd, m in shapes:
         qkv, d_o, kb = make(B, L, H, hd, m)
-        for tag in ("v3", "old"):
-            if tag == "old":
-                os.environ["B200MM_ATTN_OLD"] = "1"
+        for tag in ("v3",):
             try:
                 o, lse = ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb)
                 tf = time_it(lambda: ops.attention_fwd(qkv, B, L, H, hd, key_bias=kb))
@@ -97,8 +95,6 @@ def timing():
                 print(f"time {tag} B={B} L={L} H={H} hd={hd}: fwd {tf:.3f} ms ({ff / tf / 1e9:.0f} TF/s)  bwd {tb:.3f} ms ({fb / tb / 1e9:.0f} TF/s alg)", flush=True)
             except Exception as e:  # noqa: BLE001
                 print(f"time {tag} B={B} L={L} H={H} hd={hd}: FAILED {e}", flush=True)
-            finally:
-                os.environ.pop("B200MM_ATTN_OLD", None)
 
 
 if __name__ == "__main__":
