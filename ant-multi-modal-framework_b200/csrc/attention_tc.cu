@@ -22,6 +22,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ bool at_elect_one() {
+  uint32_t q;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(q));
+  return q != 0;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows][128 B] tile with the 128B swizzle
@@ -129,63 +134,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQrows, const __grid_con
     // Per item the steps s = (key tile j, query chunk i) run as a software pipeline: S^T/dP^T of step s+1 are issued as soon as the
     // elementwise warps have pulled step s out of TMEM (SD_EMPTY), i.e. BEFORE the accumulating MMAs of step s, so the tensor pipe
     // works on dV/dK/dQ(s) and S/dP(s+1) while the elementwise warps are busy with the exponentials of step s / s+1.
+    // Issue is done by ONE ELECTED lane (elect.sync) over warp-uniform operands, so every tcgen05.mma / commit compiles to a single
+    // uniform-datapath instruction; under a plain `lane == 0` predicate ptxas wraps each of the 28 MMAs of a step in a vote / broadcast
+    // loop (~25 instructions), which made this warp - not the tensor pipe - the bottleneck of the kernel. Descriptors are base + offset.
     const uint32_t idesc_acc = make_idesc_bf16(128, AT_HD, 0, 1);  // dV / dK : A K-major (P^T, dS^T), B MN-major (dO, Q)
     const uint32_t idesc_dq = make_idesc_bf16(128, AT_HD, 1, 1);   // dQ      : A = dS^T read MN-major, B = K_j MN-major
+    const uint64_t kd0 = make_smem_desc_sw128(smem_u32(k_sm), 16, 1024), vd0 = make_smem_desc_sw128(smem_u32(v_sm), 16, 1024);
+    const uint64_t qd0 = make_smem_desc_sw128(smem_u32(q_sm), 16, 1024), dod0 = make_smem_desc_sw128(smem_u32(do_sm), 16, 1024);
+    const uint64_t ptd0 = make_smem_desc_sw128(smem_u32(pt_sm), 16, 1024), dsd0 = make_smem_desc_sw128(smem_u32(ds_sm), 16, 1024);
+    const uint64_t qmn0 = make_smem_desc_sw128(smem_u32(q_sm), 8192, 1024), domn0 = make_smem_desc_sw128(smem_u32(do_sm), 8192, 1024);
+    const uint64_t dsmn0 = make_smem_desc_sw128(smem_u32(ds_sm), 16384, 1024), kmn0 = make_smem_desc_sw128(smem_u32(k_sm), 8192, 1024);
     const int n_steps = n_kt * n_qc;
+    const int w_last = Lq - (n_qc - 1) * AB_CW;
+    const uint32_t idesc_sd_full = make_idesc_bf16(128, AB_CW, 0, 0), idesc_sd_last = make_idesc_bf16(128, w_last, 0, 0);
     uint32_t item_cnt = 0, tile_cnt0 = 0, step_cnt0 = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt, tile_cnt0 += n_kt, step_cnt0 += n_steps) {
-      mbar_wait_relaxed(&bars[BB_QD_FULL], item_cnt & 1);
-      mbar_wait_relaxed(&bars[BB_DQ_EMPTY], (item_cnt & 1) ^ 1);  // previous item's dQ accumulators have been read out
-      auto issue_sd = [&](int s) {
-        const int j = s / n_qc, i = s - j * n_qc;
+      mbar_wait(&bars[BB_QD_FULL], item_cnt & 1);
+      mbar_wait(&bars[BB_DQ_EMPTY], (item_cnt & 1) ^ 1);  // previous item's dQ accumulators have been read out
+      // S^T / dP^T of step (j, i)
+      auto issue_sd = [&](int j, int i) {
         const uint32_t tile_cnt = tile_cnt0 + j;
         const int jb = tile_cnt & 1;
-        if (i == 0) mbar_wait_relaxed(&bars[BB_KV_FULL0 + jb], (tile_cnt >> 1) & 1);
-        const int q0 = i * AB_CW;
-        const int w = min(AB_CW, Lq - q0);
-        const uint32_t idesc_sd = make_idesc_bf16(128, w, 0, 0);
+        if (i == 0) mbar_wait(&bars[BB_KV_FULL0 + jb], (tile_cnt >> 1) & 1);
+        const uint32_t idesc_sd = i == n_qc - 1 ? idesc_sd_last : idesc_sd_full;
+        const uint64_t ka = kd0 + jb * 1024, va = vd0 + jb * 1024;             // 16 KB tiles, descriptor units of 16 B
+        const uint64_t qb = qd0 + i * (AB_CW * 8), dob = dod0 + i * (AB_CW * 8);  // AB_CW rows of 128 B
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t ka = smem_u32(k_sm + jb * 16384), va = smem_u32(v_sm + jb * 16384);
-          const uint32_t qb = smem_u32(q_sm) + q0 * 128, dob = smem_u32(do_sm) + q0 * 128;
+        if (at_elect_one()) {
 #pragma unroll
           for (int k = 0; k < AT_HD / 16; ++k) {
-            umma_bf16(tm_s, make_smem_desc_sw128(ka + k * 32, 16, 1024), make_smem_desc_sw128(qb + k * 32, 16, 1024), idesc_sd, k > 0);
-            umma_bf16(tm_dp, make_smem_desc_sw128(va + k * 32, 16, 1024), make_smem_desc_sw128(dob + k * 32, 16, 1024), idesc_sd, k > 0);
+            umma_bf16(tm_s, ka + 2 * k, qb + 2 * k, idesc_sd, k > 0);
+            umma_bf16(tm_dp, va + 2 * k, dob + 2 * k, idesc_sd, k > 0);
           }
           umma_commit(&bars[BB_SD_FULL]);
         }
         __syncwarp();
       };
-      issue_sd(0);
+      issue_sd(0, 0);
+      int j = 0, i = 0;
       for (int s = 0; s < n_steps; ++s) {
-        const int j = s / n_qc, i = s - j * n_qc;
         const uint32_t tile_cnt = tile_cnt0 + j, step_cnt = step_cnt0 + s;
         const int jb = tile_cnt & 1;
         if (s + 1 < n_steps) {
-          mbar_wait_relaxed(&bars[BB_SD_EMPTY], step_cnt & 1);  // S^T/dP^T of step s are in registers: the TMEM buffers are free
-          issue_sd(s + 1);
+          mbar_wait(&bars[BB_SD_EMPTY], step_cnt & 1);  // S^T/dP^T of step s are in registers: the TMEM buffers are free
+          if (i + 1 == n_qc) issue_sd(j + 1, 0);
+          else issue_sd(j, i + 1);
         }
-        const int q0 = i * AB_CW;
-        const int w = min(AB_CW, Lq - q0);
-        mbar_wait_relaxed(&bars[BB_PDS_FULL], step_cnt & 1);
-        if (i == 0) mbar_wait_relaxed(&bars[BB_DKV_EMPTY], (tile_cnt & 1) ^ 1);  // previous tile's dV/dK have been read out
+        const int nk = (i == n_qc - 1 ? w_last : AB_CW) >> 4;
+        const uint64_t dob = domn0 + i * (AB_CW * 8), qb = qmn0 + i * (AB_CW * 8);
+        const uint64_t ka = kmn0 + jb * 1024;
+        if (i == 0) mbar_wait(&bars[BB_DKV_EMPTY], (tile_cnt & 1) ^ 1);  // previous tile's dV/dK have been read out
+        mbar_wait(&bars[BB_PDS_FULL], step_cnt & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t ka = smem_u32(k_sm + jb * 16384);
-          const uint32_t pa = smem_u32(pt_sm), dsa = smem_u32(ds_sm);
-          const uint32_t qb = smem_u32(q_sm) + q0 * 128, dob = smem_u32(do_sm) + q0 * 128;
-          for (int kk = 0; kk < w / 16; ++kk) {
-            const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
-            umma_bf16(tm_dv, make_smem_desc_sw128(pa + aoff, 16, 1024), make_smem_desc_sw128(dob + kk * 2048, 8192, 1024), idesc_acc,
-                      (i > 0 || kk > 0));
-            umma_bf16(tm_dk, make_smem_desc_sw128(dsa + aoff, 16, 1024), make_smem_desc_sw128(qb + kk * 2048, 8192, 1024), idesc_acc,
-                      (i > 0 || kk > 0));
+        if (at_elect_one()) {
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint32_t aoff = (kk >> 2) * 1024 + (kk & 3) * 2;
+            umma_bf16(tm_dv, ptd0 + aoff, dob + kk * 128, idesc_acc, (i > 0 || kk > 0));
+            umma_bf16(tm_dk, dsd0 + aoff, qb + kk * 128, idesc_acc, (i > 0 || kk > 0));
           }
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // reduction over the 128 keys of tile j
-            umma_bf16(tm_dq + i * 64, make_smem_desc_sw128(dsa + kk * 2048, 16384, 1024), make_smem_desc_sw128(ka + kk * 2048, 8192, 1024),
-                      idesc_dq, (j > 0 || kk > 0));
+            umma_bf16(tm_dq + i * 64, dsmn0 + kk * 128, ka + kk * 128, idesc_dq, (j > 0 || kk > 0));
           umma_commit(&bars[BB_PDS_EMPTY]);
           if (i == n_qc - 1) {
             umma_commit(&bars[BB_DKV_FULL]);
@@ -197,6 +206,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQrows, const __grid_con
           }
         }
         __syncwarp();
+        if (++i == n_qc) { i = 0; ++j; }
       }
     }
   } else if (warp >= 4) {
@@ -233,8 +243,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQrows, const __grid_con
       const int64_t bh = static_cast<int64_t>(b) * p.H + h;
       sm_sync();  // previous item's readers are done with lse_sm / d_sm
       for (int i = threadIdx.x - 128; i < Lq; i += AT_SM_THREADS) {
-        lse_sm[i] = i < p.L ? p.lse[bh * p.L + i] * AT_LOG2E : INFINITY;
-        d_sm[i] = i < p.L ? p.dsum[bh * p.L + i] : 0.f;
+        lse_sm[i] = i < p.L ? -p.lse[bh * p.L + i] * AT_LOG2E : -INFINITY;  // negated: exponent = s c + (key bias + lse_sm)
+        d_sm[i] = i < p.L ? -p.dsum[bh * p.L + i] * p.scale : 0.f;          // negated and scaled: dS = P (dP scale + d_sm)
       }
       sm_sync();
       for (int j = 0; j < n_kt; ++j, ++tile_cnt) {
@@ -264,6 +274,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQrows, const __grid_con
               tmem_ld_wait8(sv[k]);
               tmem_ld_wait8(dv[k]);
             }
+            const float2 c2 = make_float2(c, c), sc2 = make_float2(p.scale, p.scale), kb2 = make_float2(kb, kb);
             // S^T / dP^T of this step now live in registers: hand the TMEM buffers back to the tensor core
             tc_fence_before();
             __syncwarp();
@@ -274,16 +285,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQrows, const __grid_con
                 const int q = q0 + (u0 + k) * 8;
                 const float4 l0 = *reinterpret_cast<const float4*>(lse_sm + q), l1 = *reinterpret_cast<const float4*>(lse_sm + q + 4);
                 const float4 d0 = *reinterpret_cast<const float4*>(d_sm + q), d1 = *reinterpret_cast<const float4*>(d_sm + q + 4);
-                const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-                float pe[8], de[8];
+                // packed fp32x2 arithmetic: per pair one FADD2 (key bias + -lse), one FFMA2 (exponent), two ex2, one FFMA2 (dP scale - D scale),
+                // one FMUL2, two packs
+                const float2 ls[4] = {make_float2(l0.x, l0.y), make_float2(l0.z, l0.w), make_float2(l1.x, l1.y), make_float2(l1.z, l1.w)};
+                const float2 dd[4] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y), make_float2(d1.z, d1.w)};
+                uint32_t pw[4], dw[4];
 #pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                  pe[x] = fast_exp2(fmaf(__uint_as_float(sv[k][x]), c, kb) - ls[x]);
-                  de[x] = pe[x] * (__uint_as_float(dv[k][x]) - dd[x]) * p.scale;
+                for (int x = 0; x < 4; ++x) {
+                  const float2 z = __ffma2_rn(make_float2(__uint_as_float(sv[k][2 * x]), __uint_as_float(sv[k][2 * x + 1])), c2, __fadd2_rn(ls[x], kb2));
+                  const float2 pe = make_float2(fast_exp2(z.x), fast_exp2(z.y));
+                  const float2 u = __ffma2_rn(make_float2(__uint_as_float(dv[k][2 * x]), __uint_as_float(dv[k][2 * x + 1])), sc2, dd[x]);
+                  const float2 de = __fmul2_rn(pe, u);
+                  pw[x] = pack_bf16x2(pe.x, pe.y);
+                  dw[x] = pack_bf16x2(de.x, de.y);
                 }
-                pk[k] = make_uint4(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
-                dk[k] = make_uint4(pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7]));
+                pk[k] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                dk[k] = make_uint4(dw[0], dw[1], dw[2], dw[3]);
               }
             }
           } else {
