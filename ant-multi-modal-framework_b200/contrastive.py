@@ -24,6 +24,12 @@ BF16 = torch.bfloat16
 
 
 def _world(group=None):
+    """(rank, world) of the contrastive batch. group == "local": no collective at all — the loss of this rank's rows only (evaluation,
+    where the reference does not gather: univl_video_ret.py:313)."""
+    if isinstance(group, str):
+        if group != "local":
+            raise ValueError(f"unknown group {group!r}")
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
@@ -65,8 +71,14 @@ class _ContrastiveFn(Function):
         rank, world = _world(group)
         B, E = a.shape
         alpha = float(torch.exp(log_scale.detach().float())) if log_scale is not None else 1.0
-        a_all, Bg = _gather_rows(a, group)
-        b_all, _ = _gather_rows(b, group)
+        # ONE all-gather per step: both modalities travel as [B, 2E] rows; the two gathered matrices are column views of
+        # the same buffer (row pitch 2E), which the TMA descriptors of the kernels take as they are
+        if world > 1:
+            ab_all, Bg = _gather_rows(torch.cat([a, b], dim=1), group)
+            a_all, b_all = ab_all[:, :E], ab_all[:, E:]
+        else:
+            a_all, Bg = _gather_rows(a, group)
+            b_all, _ = _gather_rows(b, group)
         off = rank * B
         partsA = ops.contrast_lse_partials(a, b_all[:Bg], alpha, off)   # rows: a_loc, cols: all b
         partsB = ops.contrast_lse_partials(b, a_all[:Bg], alpha, off)   # rows: b_loc, cols: all a
@@ -105,11 +117,14 @@ class _ContrastiveFn(Function):
         # local-row gradients:  da = GA · b_all,  db = GB · a_all        (B operand read MN-major: [K = Bg_pad, N = E])
         da = ops.gemm(GA, b_all, b_mn=True, out_f32=True)
         db = ops.gemm(GB, a_all, b_mn=True, out_f32=True)
-        # gathered-row gradients: d b_all = GA^T · a,  d a_all = GB^T · b    (A operand MN-major: [K = B, M = Bg_pad])
-        db_all = ops.gemm(GA, a, a_mn=True, b_mn=True, out_f32=True)
-        da_all = ops.gemm(GB, b, a_mn=True, b_mn=True, out_f32=True)
-        da = da + _scatter_grad(da_all, B, group)
-        db = db + _scatter_grad(db_all, B, group)
+        # gathered-row gradients: d b_all = GA^T · a,  d a_all = GB^T · b    (A operand MN-major: [K = B, M = Bg_pad]); both land in one
+        # [Bg_pad, 2E] buffer so that ONE reduce-scatter sends the rows of other ranks home (= GradientAllGather.backward)
+        d_all = torch.empty((GA.shape[1], 2 * E), device=a.device, dtype=torch.float32)
+        ops.gemm(GB, b, a_mn=True, b_mn=True, out_f32=True, out=d_all[:, :E])
+        ops.gemm(GA, a, a_mn=True, b_mn=True, out_f32=True, out=d_all[:, E:])
+        home = _scatter_grad(d_all, B, group)
+        da = da + home[:, :E]
+        db = db + home[:, E:]
         d_ls = dscale.reshape(()).to(scale_dtype) if has_scale else None
         return da.to(BF16), db.to(BF16), d_ls, None, None
 

@@ -407,31 +407,40 @@ class M2Encoder(nn.Module):
         fv = Fn.RowNormFn.apply(Fn.ClsLinearFn.apply(hv, _bf16(proj_vl.fc.weight), B, L))
         return f, fv
 
+    @staticmethod
+    def img_norm(img):
+        """inception_normalize (vlmo/transforms/utils.py:48, applied inside VLMo.infer_image, vlmo_module.py:17,385): (x - 0.5) / 0.5."""
+        return ((img.float() - 0.5) / 0.5).to(img.dtype)
+
     def infer_image(self, batch, mask_image=False, image_token_type_idx=1, image_embeds=None, image_masks=None):
-        """vlmo_module.py:364-405. batch["image"][0] must already be inception-normalised ((x − 0.5)/0.5, transforms/utils.py:48) —
-        a per-pixel affine map of the loader output, applied by the caller like the reference's img_norm (:385)."""
+        """vlmo_module.py:364-405, same batch dictionary as the reference: batch["image"][0] is the loader output in [0, 1]; the inception
+        normalisation of :385 is applied here (one elementwise pass over the pixels), so the method is a drop-in."""
         if mask_image:
             raise NotImplementedError("b200mm M2Encoder.infer_image: masked image modelling is not on the ITC path")
         imgkey = f"image_{image_token_type_idx - 1}" if f"image_{image_token_type_idx - 1}" in batch else "image"
-        img = batch[imgkey][0]
+        img = self.img_norm(batch[imgkey][0])
         h, B, L, _, _ = self.backbone.forward_tokens(visual_tokens=img)
         hv = self.backbone_vl.forward_tokens(h, B, L, -1)
         f, fv = self._heads(h, hv, B, L, self.itc_image_proj, self.itc_vl_image_proj)
         return {"image_feats": h.view(B, L, -1), "cls_feats": f, "cls_vlffn_feats": fv}
 
-    def infer_text(self, batch, mask_text=False):
-        """vlmo_module.py:323-362."""
+    def infer_text(self, batch, mask_text=False, with_text_embed=True):
+        """vlmo_module.py:323-362; returns the reference's keys (cls_feats, cls_vlffn_feats, text_embed = backbone.text_embed(text_ids),
+        :332) plus the language hiddens as "text_hidden". with_text_embed=False skips the embedding lookup nobody on the ITC path reads."""
         do_mlm = "_mlm" if mask_text else ""
         text_ids = batch[f"text_ids{do_mlm}"]
         text_padding_position = 1 - batch["text_masks"]
         h, B, L, drop, key_bias = self.backbone.forward_tokens(textual_tokens=text_ids, text_padding_position=text_padding_position)
         hv = self.backbone_vl.forward_tokens(h, B, L, -1, drop, key_bias)  # expert A on the language hiddens (:343)
         f, fv = self._heads(h, hv, B, L, self.itc_text_proj, self.itc_vl_text_proj)
-        return {"cls_feats": f, "cls_vlffn_feats": fv, "text_hidden": h.view(B, L, -1)}
+        ret = {"cls_feats": f, "cls_vlffn_feats": fv, "text_hidden": h.view(B, L, -1)}
+        if with_text_embed:
+            ret["text_embed"] = self.backbone.text_embed(text_ids)
+        return ret
 
     def itc_loss(self, image, text_ids, text_masks, group=None):
         """Symmetric InfoNCE on (cls_feats, logit_scale) and (cls_vlffn_feats, logit_vl_scale); similarity as m2_encoder.py:92-95."""
         i = self.infer_image({"image": [image]})
-        t = self.infer_text({"text_ids": text_ids, "text_masks": text_masks})
+        t = self.infer_text({"text_ids": text_ids, "text_masks": text_masks}, with_text_embed=False)
         return (clip_contrastive_loss(i["cls_feats"], t["cls_feats"], self.logit_scale, group)
                 + clip_contrastive_loss(i["cls_vlffn_feats"], t["cls_vlffn_feats"], self.logit_vl_scale, group))

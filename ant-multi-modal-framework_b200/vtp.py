@@ -23,7 +23,7 @@ from . import functional as Fn
 from . import ops
 from .contrastive import mil_nce_loss
 from .cross import PairScorer
-from .distributed import gather_tensor, get_rank
+from .distributed import gather_tensor, gathered_sizes, get_rank, get_world_size
 from .moco import B200MocoUtils
 from .registry import TextEncoder, VisualEncoder
 from .video import forward_img_encoder as _forward_img_encoder
@@ -146,11 +146,19 @@ class B200VideoTextRetrieval(nn.Module):
 
     # ---- level 1 -----------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def _l1_matrix(self, text_embed_l1, video_embed_l1, num_clips):
-        """get_l1_simi_matrix + reduce_clips (:199-226, :345-355) on the gathered embeddings: [Bg_text, Bg_video] f32, no gradient
-        (only the detached copy is consumed downstream: hard mining / metrics)."""
-        t = gather_tensor(text_embed_l1, method="cat", back_gradient=False, pad_tensors=True)
-        v = gather_tensor(video_embed_l1, method="cat", back_gradient=False, pad_tensors=True)
+    def _l1_matrix(self, text_embed_l1, video_embed_l1, num_clips, cal_cross=True):
+        """get_simi_logits level 'l1' + get_l1_simi_matrix + reduce_clips (:199-226, :313-327, :345-355), no gradient (only the detached
+        copy is consumed downstream: hard mining / metrics).
+          training, cal_cross : embeddings of all ranks are gathered first (:313-325) -> [Bg_text, Bg_video]
+          eval, cal_cross     : the local matrix [bsz_text, bsz_video] (no collective: ranks may evaluate different shards)
+          cal_cross == False  : inputs are aligned pairs -> the paired clip scores reduced over clips, [bsz_text]"""
+        t, v = text_embed_l1, video_embed_l1
+        if not cal_cross:
+            own = (t.float()[:, None, :] * v.view(t.shape[0], num_clips, -1).float()).sum(-1)  # [bsz_text, n_clips]
+            return own.logsumexp(-1)
+        if self.training and get_world_size() > 1:
+            t = gather_tensor(t, method="cat", back_gradient=False, pad_tensors=True)
+            v = gather_tensor(v, method="cat", back_gradient=False, pad_tensors=True)
         nv = v.shape[0]
         pad = (-nv) % 8
         vp = torch.cat([v, v.new_zeros(pad, v.shape[1])]) if pad else v
@@ -190,11 +198,12 @@ class B200VideoTextRetrieval(nn.Module):
             # forward_stage1 :369-381: MIL-NCE over the gathered batch; the [B·n, B·n] repeat is never built
             # (under data parallelism contrastive.py returns W x the rank's share: the mean over ranks is the reference's global loss and
             # DDP's gradient averaging yields its exact gradient)
-            loss = mil_nce_loss(video_embed_l1, text_embed_l1, None, n_clips=num_clips)
+            # in eval the reference does not gather (:313): the loss is that of the local matrix
+            loss = mil_nce_loss(video_embed_l1, text_embed_l1, None if self.training else "local", n_clips=num_clips)
         else:
             loss = text_embed_l1.new_zeros((), dtype=torch.float32)
         output_dict["losses"]["level1_similarity_loss"] = loss
-        output_dict["l1_simi"] = self._l1_matrix(text_embed_l1, video_embed_l1, num_clips)
+        output_dict["l1_simi"] = self._l1_matrix(text_embed_l1, video_embed_l1, num_clips, cal_cross)
         return output_dict
 
     # ---- level 2 -----------------------------------------------------------------------------------------------------------
@@ -224,7 +233,9 @@ class B200VideoTextRetrieval(nn.Module):
             l2_simi = scorer.score_pair_list(cap_embed, cap_mask, visual_embed, visual_mask, idx, idx).view(-1, 1)
         if cal_cross and l2_simi.shape[0] == l2_simi.shape[1]:
             weighted = hard and _get(self.config, "re_weight_method", None) == "median"
-            loss = scorer.level2_loss(l2_simi, output_dict["l1_simi"] if weighted else None, get_rank() * batch_size,
+            # row offset of this rank inside the gathered level-1 matrix = sum of the batch sizes of the ranks before it (:436-438)
+            beg_idx = sum(gathered_sizes(cap_embed)[: get_rank()]) if weighted and get_world_size() > 1 else 0
+            loss = scorer.level2_loss(l2_simi, output_dict["l1_simi"] if weighted else None, beg_idx,
                                       "median" if weighted else None, _get(self.config, "re_sample_method", "top_k"))
         else:
             loss = l2_simi.new_zeros(())

@@ -146,7 +146,7 @@ class _M2Step(torch.nn.Module):
         return self.m2.itc_loss(image, text, (text != 0).long(), group)
 
 
-def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0):
+def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0, image_res=0):
     from b200mm.modules import CNCLIP, CONFIGS, M2_CONFIGS, M2Encoder
 
     if name == "base_vtp-ViT-B-16":
@@ -178,6 +178,8 @@ def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0):
         return _M2Step(m2), dict(image_resolution=cfg["image_size"], vocab_size=cfg["vocab_size"], vision_layers=cfg["encoder_layers"])
 
     cfg = dict(CONFIGS[name])
+    if image_res:
+        cfg["image_resolution"] = image_res  # e.g. 336 for BASELINE.json configs[4]; positional embeddings are random-init at that size
     cfg["text_hidden_dropout_prob"] = 0.0  # the fused kernels implement p = 0; stated in `config.dropout`
     cfg["text_attention_probs_dropout_prob"] = 0.0
     torch.manual_seed(0)  # identical weights on every rank
@@ -221,7 +223,7 @@ def run_ours(args):
     b200mm._lib.check(b200mm._lib.load().b200mm_check_device(), "b200mm_check_device")
 
     B, L = args.batch, args.seq_len
-    model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act, args.keep_ln)
+    model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act, args.keep_ln, args.image_res)
     res = cfg["image_resolution"]
     step_mod = TrainStep(model)
     if world > 1 and args.micro_batch == 0:
@@ -487,6 +489,7 @@ def main():
     ap.add_argument("--model", default="ViT-L-14")
     ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU")
     ap.add_argument("--seq-len", type=int, default=77)
+    ap.add_argument("--image-res", type=int, default=0, help="override the model's image resolution (336 = BASELINE.json configs[4])")
     ap.add_argument("--ckpt-every", type=int, default=0, help="re-run every k-th ViT block in backward (0 = never)")
     ap.add_argument("--micro-batch", type=int, default=0, help="> 0: run the step through the GradCache two-pass driver with this micro-batch")
     ap.add_argument("--keep-act", type=int, default=0, help="ViT blocks that keep the activated MLP hidden instead of recomputing it (memory for time)")

@@ -41,6 +41,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False
     if residual is not None:
         d = d + residual.float()
     d = d if out_f32 else d.to(BF)
+    if out is not None:  # the kernel writes into a caller-provided (possibly strided) buffer
+        out.copy_(d)
+        d = out
     return (d, aux) if aux_out else d
 
 

@@ -36,6 +36,31 @@ WORKER = textwrap.dedent(
     sc = gather_tensor(torch.tensor(float(rank)))
     assert sc.tolist() == [float(r) for r in range(world)]
 
+    # --- pad_tensors=True with UNEQUAL row counts (antmmf/utils/distributed_utils.py:145-176): rank r holds 2 + r rows
+    from b200mm.distributed import gathered_sizes
+    n_loc = 2 + rank
+    y = (torch.arange(n_loc * 3, dtype=torch.float32).view(n_loc, 3) + 100 * rank).requires_grad_()
+    sizes = gathered_sizes(y)
+    assert sizes == [2 + r for r in range(world)]
+    gy = gather_tensor(y, method="cat", back_gradient=True, pad_tensors=True)
+    expect_rows = torch.cat([torch.arange((2 + r) * 3, dtype=torch.float32).view(2 + r, 3) + 100 * r for r in range(world)])
+    assert gy.shape == expect_rows.shape and torch.equal(gy.detach(), expect_rows), gy
+    wy = (torch.arange(1, gy.shape[0] + 1, dtype=torch.float32)[:, None] * (rank + 1)).expand_as(gy)
+    (gy * wy).sum().backward()
+    o0 = sum(sizes[:rank])
+    exp_g = sum(torch.arange(1, gy.shape[0] + 1, dtype=torch.float32)[o0:o0 + n_loc, None] * (r + 1) for r in range(world))
+    assert torch.allclose(y.grad, exp_g.expand(n_loc, 3)), (y.grad, exp_g)
+    ng = gather_tensor(y.detach(), method="cat", pad_tensors=True)
+    assert not ng.requires_grad and torch.equal(ng, expect_rows)
+    try:
+        gather_tensor(y.detach(), method="stack", pad_tensors=True)
+        raise AssertionError("stack of unequal rows must fail like the reference's torch.stack")
+    except RuntimeError:
+        pass
+    # equal sizes with pad_tensors=True take the plain path
+    z = torch.full((2, 2), float(rank))
+    assert torch.equal(gather_tensor(z, method="cat", pad_tensors=True), torch.cat([torch.full((2, 2), float(r)) for r in range(world)]))
+
     # --- padded gather / reduce-scatter helpers
     a = torch.full((3, 4), float(rank + 1))
     all_a, Bg = _gather_rows(a, None)

@@ -101,7 +101,10 @@ def _check_against(m, fx_sd, image, ids, masks, heads, golden=None, xpos=None, m
     sd16, (o_hi, o_ht, o_fi, o_ft, o_fvi, o_fvt), o_loss = _oracle(fx_sd, image, ids, masks, heads, xpos=xpos)
     # calibrator: the same oracle arithmetic in bf16 torch eager on the GPU (the reference modules after .cuda().bfloat16())
     sdb, _, _ = _oracle(fx_sd, image, ids, masks, heads, device="cuda", dtype=BF, xpos=xpos)
-    img = m.infer_image({"image": [image.cuda()]})
+    # the module applies the reference's inception normalisation (x - 0.5) / 0.5 itself (vlmo_module.py:385); the golden tensors are the
+    # already normalised backbone inputs, so the loader-side image is its inverse image
+    raw = (image * 0.5 + 0.5)
+    img = m.infer_image({"image": [raw.cuda()]})
     txt = m.infer_text({"text_ids": ids.cuda(), "text_masks": masks.cuda()})
     assert img["cls_feats"].dtype == BF and img["cls_feats"].is_cuda
     # hidden states after the final layer_norm; padded text rows are garbage-in-garbage-out in the reference too (they only
@@ -113,7 +116,7 @@ def _check_against(m, fx_sd, image, ids, masks, heads, golden=None, xpos=None, m
     if golden is not None:  # + weight rounding
         assert rel_l2(img["cls_feats"], golden["img_f"]) < 2e-2 and rel_l2(txt["cls_feats"], golden["txt_f"]) < 2e-2
         assert rel_l2(img["cls_vlffn_feats"], golden["img_fv"]) < 2e-2 and rel_l2(txt["cls_vlffn_feats"], golden["txt_fv"]) < 2e-2
-    loss = m.itc_loss(image.cuda(), ids.cuda(), masks.cuda())
+    loss = m.itc_loss(raw.cuda(), ids.cuda(), masks.cuda())
     assert abs(float(loss) - float(o_loss)) < 2e-2 * max(1.0, abs(float(o_loss))), (float(loss), float(o_loss))
     if golden is not None:
         assert abs(float(loss) - float(golden["loss"])) < 3e-2 * max(1.0, abs(float(golden["loss"])))

@@ -34,8 +34,11 @@ def test_m2_glue_reproduces_reference_golden(golden_dir, name, checkpoint, keep)
     m.set_grad_checkpointing(checkpoint)
     m.set_keep_activation(keep)
     with emulated_ops.patched():
-        img = m.infer_image({"image": [fx["image"]]})
+        img = m.infer_image({"image": [fx["image"] * 0.5 + 0.5]})  # infer_image applies (x - 0.5) / 0.5 like vlmo_module.py:385
         txt = m.infer_text({"text_ids": fx["ids"], "text_masks": fx["masks"]})
+        # the reference's return keys (vlmo_module.py:355-359, :399-403): text_embed = backbone.text_embed(text_ids)
+        assert set(img) >= {"image_feats", "cls_feats", "cls_vlffn_feats"} and set(txt) >= {"cls_feats", "cls_vlffn_feats", "text_embed"}
+        assert torch.equal(txt["text_embed"], m.backbone.text_embed(fx["ids"]))
         assert rel_l2(img["image_feats"], fx["image_hidden"]) < 1.5e-2
         assert rel_l2(txt["text_hidden"], fx["text_hidden"]) < 1.5e-2
         for got, key in [(img["cls_feats"], "img_f"), (txt["cls_feats"], "txt_f"), (img["cls_vlffn_feats"], "img_fv"), (txt["cls_vlffn_feats"], "txt_fv")]:
