@@ -358,7 +358,12 @@ def run_ours(args):
                          "traffic": dominant.get("traffic") if dominant else None, "dominant_launch": dominant,
                          "whole_step_frac": round(pairs_per_s / world * fpp / 1e12 / peak_tf, 4) if fpp else None},
         }
-        if world == 1 and not args.no_cpu_baseline and args.model in FLOP_PER_PAIR and not args.model.startswith("M2"):  # the oracle port of the headline path
+        headline = args.model in FLOP_PER_PAIR and not args.model.startswith(("M2", "base_vtp"))
+        if world == 1 and not args.no_gpu_baseline and headline and not args.image_res:
+            del step_mod, model
+            torch.cuda.empty_cache()
+            out["gpu_eager_baseline"] = gpu_eager_baseline(args, device)
+        if world == 1 and not args.no_cpu_baseline and headline:
             out["cpu_baseline"] = cpu_baseline(args, steps=2, warmup=0)  # ~10 s of CPU work at batch 16 on 16 cores
     if world > 1:
         dist.barrier()
@@ -430,43 +435,116 @@ def write_profile(args, gemm_prof, step, image_d, text_d, B):
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"op_profile_b{B}.json"), "w"), indent=1)
 
 
+def _reference_cnclip(args):
+    """The UNMODIFIED reference CNCLIP (antmmf/modules/vision/backbone/clip/cn_model.py) imported from baseline/_ref/ — the byte copies
+    baseline/install_ref.py makes of the reference's plain-PyTorch files (sha256 in baseline/_ref/MANIFEST.json). None when the copies are
+    absent (then the oracle port is timed instead)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_import
+    finally:
+        sys.path.pop(0)
+    if not ref_import.available():
+        return None
+    return ref_import.build_cnclip(args.model, seed=0, dropout=0.0)
+
+
+def gpu_eager_baseline(args, device):
+    """SURVEY.md §8d "GPU comparison point": the reference's own modules after `.cuda().bfloat16()` under eager PyTorch on the SAME GPU
+    (nn.MultiheadAttention -> torch's fused SDPA, BertSelfAttention's matmul-softmax, F.cross_entropy on materialised logits), fwd + bwd at a
+    batch that fits eager's activation memory. Same model / sequence length / synthetic data as the B200 arm."""
+    model = _reference_cnclip(args)
+    if model is None:
+        return {"unavailable": "baseline/_ref not installed"}
+    model = model.to(device).to(torch.bfloat16).train()
+    Bc = args.eager_batch
+    cfg_res = model.visual.input_resolution if hasattr(model.visual, "input_resolution") else 224
+    image, text = synth_batch(Bc, cfg_res, args.seq_len, model.bert.embeddings.word_embeddings.num_embeddings, 1234)
+    image, text = image.to(device).to(torch.bfloat16), text.to(device)
+    target = torch.arange(Bc, device=device)
+
+    def one_step():
+        for p_ in model.parameters():
+            p_.grad = None
+        _, _, lpi, lpt = model(image, text)
+        loss = 0.5 * (torch.nn.functional.cross_entropy(lpi.float(), target) + torch.nn.functional.cross_entropy(lpt.float(), target))
+        loss.backward()
+        return loss
+
+    try:
+        for _ in range(2):
+            one_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            one_step()
+        e1.record()
+        torch.cuda.synchronize()
+    except torch.OutOfMemoryError:
+        return {"unavailable": f"eager reference modules run out of memory at batch {Bc}"}
+    ms = e0.elapsed_time(e1) / 3
+    return {"value": round(Bc / ms * 1e3, 1), "unit": "pairs/s", "ms_per_step": round(ms, 2), "batch": Bc,
+            "kind": "unmodified reference CNCLIP (baseline/_ref) .cuda().bfloat16(), eager PyTorch incl. torch SDPA inside nn.MultiheadAttention; 3 steps after 2 warm-up"}
+
+
 def cpu_baseline(args, steps, warmup):
-    """The oracle port (oracle/restated.py, fp32 eager PyTorch on the host cores) on a BOUNDED sample of the workload:
-    same model/config/sequence length, batch `cpu_batch` instead of 1024."""
+    """The reference's CPU path on a BOUNDED sample of the workload (same model / config / sequence length, batch `cpu_batch` instead of
+    1024), all host threads: the reference's own modules from baseline/_ref/ when they are installed (kind "reference": CNCLIP.forward +
+    the symmetric cross-entropy of its logits + backward, fp32 eager PyTorch), else the oracle port oracle/restated.py (kind "port")."""
     from b200mm.modules import CONFIGS
-    from oracle import restated
 
     cfg = dict(CONFIGS[args.model])
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     Bc = args.cpu_batch
-    torch.manual_seed(0)
-    from b200mm.modules import CNCLIP
-
-    model = CNCLIP(**cfg)  # parameter container only (reference init); the arithmetic below is the oracle's
-    sd = {k: v.detach().clone().requires_grad_(torch.is_floating_point(v)) for k, v in model.state_dict().items()}
-    del model
     image, text = synth_batch(Bc, cfg["image_resolution"], args.seq_len, cfg["vocab_size"], 1234)
-    vh = cfg["vision_width"] // cfg.get("vision_head_width", 64)
+    ref_model = _reference_cnclip(args)
+    if ref_model is not None:
+        ref_model = ref_model.float().train()
+        target = torch.arange(Bc)
+
+        def one_step():
+            for p_ in ref_model.parameters():
+                p_.grad = None
+            _, _, lpi, lpt = ref_model(image, text)
+            loss = 0.5 * (torch.nn.functional.cross_entropy(lpi, target) + torch.nn.functional.cross_entropy(lpt, target))
+            loss.backward()
+
+        kind, what = "reference", "unmodified reference CNCLIP from baseline/_ref (cn_model.py / model.py / modeling_bert.py), fp32 eager"
+    else:
+        from b200mm.modules import CNCLIP
+        from oracle import restated
+
+        torch.manual_seed(0)
+        model = CNCLIP(**cfg)  # parameter container only (reference init); the arithmetic below is the oracle's
+        sd = {k: v.detach().clone().requires_grad_(torch.is_floating_point(v)) for k, v in model.state_dict().items()}
+        del model
+        vh = cfg["vision_width"] // cfg.get("vision_head_width", 64)
+
+        def one_step():
+            for v in sd.values():
+                v.grad = None
+            _, _, logits, _ = restated.cnclip_forward(sd, image, text, vh, cfg["text_num_attention_heads"])
+            restated.symmetric_info_nce(logits).backward()
+
+        kind, what = "port", "oracle/restated.py fp32 eager"
     times = []
     for i in range(warmup + steps):
-        for v in sd.values():
-            v.grad = None
         t0 = time.perf_counter()
-        _, _, logits, _ = restated.cnclip_forward(sd, image, text, vh, cfg["text_num_attention_heads"])
-        restated.symmetric_info_nce(logits).backward()
+        one_step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     best = min(times)
-    return {"value": round(Bc / best, 3), "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": f"oracle/restated.py fp32 eager, same model/seq_len, batch {Bc} instead of {args.batch}; best of {steps} step(s) after {warmup} warm-up",
+    return {"value": round(Bc / best, 3), "unit": "pairs/s", "cores": threads, "kind": kind,
+            "sample": f"{what}, same model/seq_len, batch {Bc} instead of {args.batch}; best of {steps} step(s) after {warmup} warm-up",
             "s_per_step": round(best, 2)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host CPU cores. /root/reference (pure Python, needs
-    omegaconf & co to import as a package) does not travel to the GPU box, so the timed object is the oracle port."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores — the unmodified modules installed under
+    baseline/_ref/ by baseline/install_ref.py (they travel to the GPU box with the snapshot); the oracle port only if they are absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -474,7 +552,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"CNCLIP {args.model} + BERT-base fwd + symmetric InfoNCE + bwd, CPU eager fp32, bounded sample batch {args.cpu_batch}",
+           "config": {"workload": f"CNCLIP {args.model} + BERT-base fwd + symmetric InfoNCE + bwd, CPU eager fp32 ({cb['kind']}), bounded sample batch {args.cpu_batch}",
                       "model": args.model, "seq_len": args.seq_len},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -496,6 +574,8 @@ def main():
     ap.add_argument("--keep-ln", type=int, default=16, help="ViT blocks that keep both LayerNorm outputs instead of recomputing them (memory for time)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU-baseline sample (fp32 eager needs ~0.6 GB of host RAM per pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch bf16 run of the reference modules on the same GPU")
+    ap.add_argument("--eager-batch", type=int, default=128, help="batch of the eager GPU baseline (eager keeps every activation)")
     ap.add_argument("--profile", action="store_true", help="write gpurun_out/op_profile_b<B>.json (per-op CUDA-event breakdown)")
     ap.add_argument("--skip-e2e", action="store_true", help="diagnostics only: skip the host-input leg")
     args = ap.parse_args()
