@@ -1,0 +1,117 @@
+"""Parity at BASELINE depth (GPU): the real CONFIGS["ViT-L-14"] towers (24 ViT-L/14 blocks + 12 BERT-base layers, the configs[1] model)
+at B = 4 against the fp32 CPU oracle on the same bf16-rounded weights, with the eager-bf16 run of the same oracle arithmetic on the GPU
+as the calibrator (= what the reference's modules produce after `.cuda().bfloat16()`).
+
+What is pinned (VERDICT r1 "no parity at BASELINE depth"): error growth over 24 + 12 layers. The measured rel-L2 of every output and of
+every parameter gradient is appended to gpurun_out/parity_measured.jsonl (rendered into profiles/parity_r02.md by tools/parity_report.py);
+the bounds asserted below are 1.5 x the values measured on B200 in round 2 (see that file) — bf16 storage makes the north star's 1e-3
+unattainable against an fp32 oracle (one bf16 rounding is 2^-9 = 2e-3 relative), so the bar stated here is: no further from the fp32
+oracle than 1.5 x the measured bf16 pipeline error, and never worse than 1.5 x the eager-bf16 reference arithmetic.
+"""
+import json
+import os
+import time
+
+import pytest
+import torch
+
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# measured on B200 (profiles/parity_r02.md): the asserted bound = 1.5 x measured
+BOUND_FEATURES = 1.5 * 1.0e-2
+BOUND_LOSS_ABS = 1.5 * 1.0e-2
+BOUND_GRAD_MEDIAN = 1.5 * 2.0e-2
+BOUND_GRAD_WORST_VS_EAGER = 1.5
+
+
+def rel_l2(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-12))
+
+
+def _record(entry):
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps(entry) + "\n")
+    except OSError:
+        pass
+
+
+def test_vit_l14_bert_base_full_depth_vs_oracle():
+    from b200mm.modules import CNCLIP
+    from b200mm.modules.cnclip import CONFIGS
+
+    cfg = dict(CONFIGS["ViT-L-14"], text_attention_probs_dropout_prob=0.0, text_hidden_dropout_prob=0.0)
+    torch.manual_seed(1234)
+    model = CNCLIP(**cfg)
+    B, L = 4, 32
+    g = torch.Generator().manual_seed(7)
+    image = torch.randn(B, 3, 224, 224, generator=g)
+    text = torch.randint(1, cfg["vocab_size"], (B, L), generator=g)
+    text[:, 0] = 101
+    text[1, 20:] = 0
+    text[3, 9:] = 0
+    sd = model.state_dict()
+    vh, th = cfg["vision_width"] // cfg["vision_head_width"], cfg["text_num_attention_heads"]
+
+    # fp32 oracle on the bf16-rounded weights and inputs (CPU)
+    t0 = time.time()
+    sd16 = {k: (v.to(BF).float().clone().requires_grad_(True) if torch.is_floating_point(v) else v) for k, v in sd.items()}
+    o_img, o_txt, o_logits, _ = restated.cnclip_forward(sd16, image.to(BF).float(), text, vh, th)
+    o_loss = restated.symmetric_info_nce(o_logits)
+    o_loss.backward()
+    t_oracle = time.time() - t0
+
+    # calibrator: same arithmetic in eager bf16 on the GPU
+    sdb = {k: (v.detach().to(BF).cuda().requires_grad_(True) if torch.is_floating_point(v) else v.cuda()) for k, v in sd.items()}
+    e_img, e_txt, e_logits, _ = restated.cnclip_forward(sdb, image.cuda().to(BF), text.cuda(), vh, th)
+    e_loss = restated.symmetric_info_nce(e_logits.float())
+    e_loss.backward()
+
+    m = model.cuda().to(BF).train()
+    img, txt = m.encode_normalized(image.cuda(), text.cuda())
+    loss = m.contrastive_loss(image.cuda(), text.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    feats = {"image_features": (rel_l2(img, o_img), rel_l2(e_img, o_img)), "text_features": (rel_l2(txt, o_txt), rel_l2(e_txt, o_txt))}
+    loss_err = (abs(float(loss) - float(o_loss)), abs(float(e_loss) - float(o_loss)))
+    ours, eager = {}, {}
+    for n, p in m.named_parameters():
+        ref = sd16[n].grad
+        if ref is None or float(ref.abs().max()) < 1e-7 or n == "logit_scale":
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        ours[n] = rel_l2(p.grad, ref)
+        eager[n] = rel_l2(sdb[n].grad, ref)
+    so, se = sorted(ours.values()), sorted(eager.values())
+    med, med_e = so[len(so) // 2], se[len(se) // 2]
+    worst_n = max(ours, key=lambda n: ours[n] / max(eager[n], 1e-4))
+    by_depth = {}
+    for blk in (0, 11, 23):
+        ks = [n for n in ours if n.startswith(f"visual.transformer.resblocks.{blk}.") and n.endswith("weight") and ours[n] == ours[n]]
+        if ks:
+            by_depth[f"vit_block_{blk}"] = (max(ours[k] for k in ks), max(eager[k] for k in ks))
+    for blk in (0, 11):
+        ks = [n for n in ours if n.startswith(f"bert.encoder.layer.{blk}.") and n.endswith("weight")]
+        if ks:
+            by_depth[f"bert_layer_{blk}"] = (max(ours[k] for k in ks), max(eager[k] for k in ks))
+    _record({"test": "vit_l14_bert_base_full_depth", "B": B, "L_text": L, "oracle_seconds": round(t_oracle, 1), "features": feats,
+             "loss": {"ours": float(loss), "oracle": float(o_loss), "eager_bf16": float(e_loss)}, "loss_abs_err": loss_err,
+             "grad_rel_l2": {"n_params": len(ours), "median": (med, med_e), "max": (so[-1], se[-1]),
+                             "p90": (so[int(0.9 * len(so))], se[int(0.9 * len(se))]),
+                             "worst_vs_eager": {"name": worst_n, "ours": ours[worst_n], "eager": eager[worst_n]}},
+             "by_depth_max_weight_grad": by_depth})
+
+    for k, (mine, eag) in feats.items():
+        assert mine < BOUND_FEATURES, (k, mine, eag)
+    assert loss_err[0] < BOUND_LOSS_ABS * max(1.0, abs(float(o_loss))), loss_err
+    assert med < max(BOUND_GRAD_MEDIAN, BOUND_GRAD_WORST_VS_EAGER * med_e), (med, med_e)
+    for n in ours:
+        assert ours[n] < max(BOUND_GRAD_MEDIAN, BOUND_GRAD_WORST_VS_EAGER * eager[n]), (n, ours[n], eager[n])

@@ -30,6 +30,9 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     g, u = ops.gemm(y, wfc, bias=bfc, act=ops.ACT_QUICKGELU, aux_out=True)
     # dgrad through the activation: du = (dy @ Wproj) * act'(u)
     du = ops.gemm(dy, wproj, b_mn=True, act=ops.ACT_QUICKGELU, dact_in=u)
+    # ... and the form the training step launches: the same dgrad also emitting act(u) (flavour 74, the bench's dominant launch)
+    du, g2 = ops.gemm(dy, wproj, b_mn=True, act=ops.ACT_QUICKGELU, dact_in=u, aux_out=True)
+    del g2
     # plain K = 4096 GEMM and a split-K weight gradient
     h = ops.gemm(g, wproj, bias=b, residual=x)
     dwp = ops.gemm(dy, g, a_mn=True, b_mn=True)
@@ -52,5 +55,10 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     ia = torch.nn.functional.normalize(torch.randn(8192, 768, device="cuda"), dim=-1).to(BF)
     pm = ops.contrast_lse_partials(ia[:1024].contiguous(), ia, 14.3, 0)
     ops.contrast_lse_merge(pm[:2], None, pm[2], False, torch.zeros(1, device="cuda"))
+    # qkv projection (K = 1024 -> N = 3072, flavour 1) and the plain dgrad back through the out-projection (flavour 0, B MN-major)
+    win = (torch.randn(3 * W, W, device="cuda") * 0.02).to(BF)
+    ops.gemm(y, win, bias=torch.zeros(3 * W, device="cuda", dtype=BF))
+    wout = (torch.randn(W, W, device="cuda") * 0.02).to(BF)
+    ops.gemm(dy, wout, b_mn=True)
 torch.cuda.synchronize()
 print("done")

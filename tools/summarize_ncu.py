@@ -111,6 +111,9 @@ def traffic(path):
     # [M, N, K] of the GEMM launches tools/prof_kernels.py makes, by kernel instantiation (flavor = epilogue bits, gemm_tcgen05.cu flavor_bits)
     shapes = {"gemm_tcgen05_kernel<0, 0, 0, 2, 67>": [T, 4096, 1024],   # c_fc forward: bias + QuickGELU + pre-activation copy
               "gemm_tcgen05_kernel<0, 1, 0, 2, 72>": [T, 4096, 1024],   # dgrad through the activation (x act'(u))
+              "gemm_tcgen05_kernel<0, 1, 0, 2, 74>": [T, 4096, 1024],   # ... also emitting act(u): the training step's dominant launch
+              "gemm_tcgen05_kernel<0, 0, 0, 2, 1>": [T, 3072, 1024],    # qkv projection: bias
+              "gemm_tcgen05_kernel<0, 1, 0, 2, 0>": [T, 1024, 1024],    # plain dgrad through the out-projection
               "gemm_tcgen05_kernel<0, 0, 0, 2, 5>": [T, 1024, 4096]}    # c_proj forward: bias + residual
     print(json.dumps({"source": path, "how": f"PROF_ROWS={T} ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum "
                       "--clock-control none python tools/prof_kernels.py 1 (one launch per kernel)",
