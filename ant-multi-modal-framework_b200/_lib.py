@@ -5,7 +5,7 @@ raises — there is no CPU or eager-PyTorch fallback on the product path.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mm.so")
@@ -26,6 +26,7 @@ class GemmArgs(Structure):
         ("residual", c_void_p), ("ldr", c_int64),
         ("splits", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("drop_p", c_float), ("drop_seed", c_uint64),
     ]
 
 
@@ -45,6 +46,12 @@ SIGNATURES = {
     "b200mm_embed_layernorm_fwd": (c_int32, [_P, _I64P, _P, c_int64, _P, _I64P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P]),
     "b200mm_attention_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P]),
     "b200mm_attention_bwd": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P]),
+    "b200mm_attention_fwd_dropout": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float,
+                                               c_float, c_uint64, _P]),
+    "b200mm_attention_bwd_dropout": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,
+                                               c_int32, c_float, c_float, c_uint64, _P]),
+    "b200mm_attention_dropout_mask": (c_int32, [_P, c_int32, c_int32, c_int32, c_float, c_uint64, _P]),
+    "b200mm_dropout": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int32, c_float, c_uint64, _P]),
     "b200mm_contrast_num_tiles": (c_int32, [c_int64]),
     "b200mm_contrast_lse_partials": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P]),
     "b200mm_contrast_lse_merge": (c_int32, [_P, _P, c_int32, _P, _P, c_int32, _P, c_int32, _P, _P, c_int64, _P]),

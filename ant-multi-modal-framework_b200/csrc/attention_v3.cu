@@ -170,9 +170,12 @@ struct A3FwdParams {
   int32_t NS, resident;
   int32_t q_off, k_off, v_off;
   float scale_log2;  // softmax scale * log2(e)
+  uint32_t drop_thr;     // DROP kernels: probability (q, k) of item (b, h) is zeroed iff hash < drop_thr (common.cuh)
+  float drop_inv_keep;   // 1 / (1 - p), applied to O in the epilogue
+  uint64_t drop_seed;
 };
 
-template <bool HAS_BIAS>
+template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKV,
                  const A3FwdParams p) {
@@ -415,6 +418,13 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int rot = (tail && rot_tail) ? (it & 3) : 0;
       const int rows = tail ? p.r_last : 128;
       const bool active = rot_tail && tail ? quarter == rot : quarter * 32 < rows;  // warp-uniform: any valid row in this warp
+      // dropout on the probabilities: stream = (batch, head) item, index = query * L + key. The row sum l stays that of the un-dropped
+      // softmax (dropout follows the normalisation, modeling_bert.py:155-158); the 1 / (1 - p) factor is applied to O in the epilogue.
+      uint32_t drop_key = 0u, drop_row = 0u;
+      if (DROP) {
+        drop_key = drop_stream_key(p.drop_seed, static_cast<uint64_t>(blockIdx.x + it * gridDim.x));
+        drop_row = static_cast<uint32_t>(tk * 128 + r - 32 * rot) * static_cast<uint32_t>(p.L);
+      }
       if (HAS_BIAS && bias_item != it) {
         const int item = blockIdx.x + it * gridDim.x;
         const int b = item / p.H;
@@ -526,7 +536,13 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
               for (int q = 0; q < 16; q += 2) {
                 acc = __fadd2_rn(acc, make_float2(e[(c - 1) & 1][q], e[(c - 1) & 1][q + 1]));
-                pk[q >> 1] = pack_bf16x2(e[(c - 1) & 1][q], e[(c - 1) & 1][q + 1]);
+                if (DROP) {
+                  const uint32_t idx = drop_row + static_cast<uint32_t>(j * p.KB + (c - 1) * 16 + q);
+                  pk[q >> 1] = pack_bf16x2(drop_keep(drop_key, idx, p.drop_thr) ? e[(c - 1) & 1][q] : 0.f,
+                                           drop_keep(drop_key, idx + 1, p.drop_thr) ? e[(c - 1) & 1][q + 1] : 0.f);
+                } else {
+                  pk[q >> 1] = pack_bf16x2(e[(c - 1) & 1][q], e[(c - 1) & 1][q + 1]);
+                }
               }
               a3_tmem_st8(t_s + (c - 1) * 8, pk);
             }
@@ -561,7 +577,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       if (active) {
         const float2 st = stats[(w * 2 + (u & 1)) * 128 + r];
-        const float inv = 1.f / st.y;
+        const float inv = DROP ? p.drop_inv_keep / st.y : 1.f / st.y;
         const uint32_t t_o = tmem_base + 256 + w * 128 + lane_addr;
         for (int c = 0; c < p.hd / 16; ++c) {
           uint32_t v[16];
@@ -638,9 +654,12 @@ struct A3BwdParams {
   int32_t x0_off, x1_off, y0_off, y1_off;  // column offsets of the four operands inside their matrices
   int32_t q_off, k_off, v_off;
   float scale, scale_log2;
+  uint32_t drop_thr;     // DROP kernels: see A3FwdParams
+  float drop_inv_keep;
+  uint64_t drop_seed;
 };
 
-template <int MODE, bool HAS_BIAS>
+template <int MODE, bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn3_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX0t, const __grid_constant__ CUtensorMap tmX1,
                  const __grid_constant__ CUtensorMap tmX1t, const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ CUtensorMap tmY1,
@@ -889,6 +908,9 @@ attn3_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
         rc1 = row_ok ? -p.dsum[bh * p.L + orow] * p.scale : 0.f;
       }
       const float2 r0 = make_float2(rc0, rc0), r1 = make_float2(rc1, rc1);
+      // dropout on the probabilities, regenerated from the seed: index = query * L + key (row = key in dK/dV mode, query in dQ mode)
+      uint32_t drop_key = 0u;
+      if (DROP) drop_key = drop_stream_key(p.drop_seed, static_cast<uint64_t>(item));
       for (int i = 0; i < p.n_in; ++i, ++f) {
         const int t = f & 1;
         const int nbj = i == p.n_in - 1 ? p.nb_last : p.NB;
@@ -972,7 +994,37 @@ attn3_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
                   ua = __ffma2_rn(a3_u2f2(d[k][x], d[k][x + 1]), sc2, r1);
                   ub = __ffma2_rn(a3_u2f2(d[k][x + 2], d[k][x + 3]), sc2, r1);
                 }
-                const float2 pa = make_float2(pe[k][x], pe[k][x + 1]), pb = make_float2(pe[k][x + 2], pe[k][x + 3]);
+                float2 pa = make_float2(pe[k][x], pe[k][x + 1]), pb = make_float2(pe[k][x + 2], pe[k][x + 3]);
+                if (DROP) {
+                  // dS = P o (m dP / (1-p) - D) scale,  dV += (P o m / (1-p))^T dO  with m the keep mask: recompute ua / ub with the masked dP
+                  const uint32_t L_ = static_cast<uint32_t>(p.L), o_ = static_cast<uint32_t>(orow), cc = static_cast<uint32_t>(col0 + x);
+                  bool kp[4];
+#pragma unroll
+                  for (int y = 0; y < 4; ++y)
+                    kp[y] = drop_keep(drop_key, MODE == A3_MODE_DKV ? (cc + y) * L_ + o_ : o_ * L_ + cc + y, p.drop_thr);
+                  const float ik = p.drop_inv_keep;
+                  float2 dterm_a, dterm_b;
+                  if (MODE == A3_MODE_DKV) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(colc1 + col0 + x);
+                    dterm_a = make_float2(d4.x, d4.y);
+                    dterm_b = make_float2(d4.z, d4.w);
+                  } else {
+                    dterm_a = r1;
+                    dterm_b = r1;
+                  }
+                  ua.x = fmaf(kp[0] ? __uint_as_float(d[k][x]) * ik : 0.f, p.scale, dterm_a.x);
+                  ua.y = fmaf(kp[1] ? __uint_as_float(d[k][x + 1]) * ik : 0.f, p.scale, dterm_a.y);
+                  ub.x = fmaf(kp[2] ? __uint_as_float(d[k][x + 2]) * ik : 0.f, p.scale, dterm_b.x);
+                  ub.y = fmaf(kp[3] ? __uint_as_float(d[k][x + 3]) * ik : 0.f, p.scale, dterm_b.y);
+                  const float2 da_ = __fmul2_rn(pa, ua), db_ = __fmul2_rn(pb, ub);
+                  if (MODE == A3_MODE_DKV) {
+                    pk[x >> 1] = pack_bf16x2(kp[0] ? pa.x * ik : 0.f, kp[1] ? pa.y * ik : 0.f);
+                    pk[(x >> 1) + 1] = pack_bf16x2(kp[2] ? pb.x * ik : 0.f, kp[3] ? pb.y * ik : 0.f);
+                  }
+                  dk[x >> 1] = pack_bf16x2(da_.x, da_.y);
+                  dk[(x >> 1) + 1] = pack_bf16x2(db_.x, db_.y);
+                  continue;
+                }
                 const float2 da = __fmul2_rn(pa, ua), db = __fmul2_rn(pb, ub);
                 if (MODE == A3_MODE_DKV) {
                   pk[x >> 1] = pack_bf16x2(pa.x, pa.y);
@@ -1116,7 +1168,9 @@ static bool a3_plan_fwd(int L, int hd, bool has_bias, A3Plan& pl) {
 }
 
 int attention_fwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
-                     const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, cudaStream_t stream) {
+                     const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, float drop_p, uint64_t drop_seed,
+                     cudaStream_t stream) {
+  B200MM_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || L <= 65535), B200MM_ERR_SHAPE, "attention_fwd: drop_p=%f L=%d", drop_p, L);
   B200MM_REQUIRE(head_dim % 16 == 0 && head_dim >= 16 && head_dim <= 128, B200MM_ERR_SHAPE,
                  "attention_fwd: head_dim %d not supported (multiples of 16 up to 128)", head_dim);
   A3Plan pl;
@@ -1136,8 +1190,13 @@ int attention_fwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
   p.n_qt = pl.n_outer; p.r_last = pl.r_last; p.KB = pl.KB; p.n_blk = pl.n_blk; p.kb_last = pl.kb_last;
   p.NS = pl.NS; p.resident = pl.resident; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off;
   p.scale_log2 = scale * A3_LOG2E;
+  const bool drop = drop_p > 0.f;
+  p.drop_thr = drop ? drop_threshold(drop_p) : 0u;
+  p.drop_inv_keep = drop ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
   const int grid = std::min(B * H, sm_count());
-  auto kern = key_bias ? attn3_fwd_kernel<true> : attn3_fwd_kernel<false>;
+  auto kern = drop ? (key_bias ? attn3_fwd_kernel<true, true> : attn3_fwd_kernel<false, true>)
+                   : (key_bias ? attn3_fwd_kernel<true, false> : attn3_fwd_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
   if (e != cudaSuccess) {
     set_last_error("attention_fwd: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
@@ -1180,7 +1239,7 @@ static bool a3_plan_bwd(int mode, int L, int hd, A3Plan& pl) {
 template <int MODE>
 static int a3_launch_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* d_o, int64_t ldo,
                          const float* lse, const float* dsum, const float* key_bias, void* dqkv, int32_t B, int32_t H, int32_t L, int32_t hd,
-                         float scale, cudaStream_t stream) {
+                         float scale, float drop_p, uint64_t drop_seed, cudaStream_t stream) {
   A3Plan pl;
   B200MM_REQUIRE(a3_plan_bwd(MODE, L, hd, pl), B200MM_ERR_SHAPE, "attention_bwd: no tiling for L=%d head_dim=%d", L, hd);
   const uint64_t T = static_cast<uint64_t>(B) * L;
@@ -1203,8 +1262,13 @@ static int a3_launch_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_o
   p.NB = pl.KB; p.n_in = pl.n_blk; p.nb_last = pl.kb_last; p.NS = pl.NS; p.resident = pl.resident;
   p.x0_off = x0off; p.x1_off = x1off; p.y0_off = y0off; p.y1_off = y1off;
   p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.scale = scale; p.scale_log2 = scale * A3_LOG2E;
+  const bool drop = drop_p > 0.f;
+  p.drop_thr = drop ? drop_threshold(drop_p) : 0u;
+  p.drop_inv_keep = drop ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
   const int grid = std::min(B * H, sm_count());
-  auto kern = key_bias ? attn3_bwd_kernel<MODE, true> : attn3_bwd_kernel<MODE, false>;
+  auto kern = drop ? (key_bias ? attn3_bwd_kernel<MODE, true, true> : attn3_bwd_kernel<MODE, false, true>)
+                   : (key_bias ? attn3_bwd_kernel<MODE, true, false> : attn3_bwd_kernel<MODE, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
   if (e != cudaSuccess) {
     set_last_error("attention_bwd: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
@@ -1220,9 +1284,10 @@ int attention_bwd_merged(const void* qkv, int64_t ld, int32_t q_off, int32_t k_o
 
 int attention_bwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o, int64_t ldo,
                      const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H, int32_t L, int32_t head_dim,
-                     float scale, cudaStream_t stream) {
+                     float scale, float drop_p, uint64_t drop_seed, cudaStream_t stream) {
   B200MM_REQUIRE(head_dim % 16 == 0 && head_dim >= 16 && head_dim <= 128, B200MM_ERR_SHAPE,
                  "attention_bwd: head_dim %d not supported (multiples of 16 up to 128)", head_dim);
+  B200MM_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || L <= 65535), B200MM_ERR_SHAPE, "attention_bwd: drop_p=%f L=%d", drop_p, L);
   const int64_t T = static_cast<int64_t>(B) * L;
   attn3_dsum_kernel<<<static_cast<unsigned>(std::min<int64_t>(ceil_div(T, 8), 148 * 64)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(o),
                                                                                     reinterpret_cast<const __nv_bfloat16*>(d_o), ldo, dsum, T, H, L,
@@ -1231,11 +1296,16 @@ int attention_bwd_v3(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, 
   if (rc) return rc;
   // head_dim 64 and <= 288 tokens: dQ, dK and dV of an item fit the 512 TMEM columns together -> one merged kernel, 5 GEMMs and one exp
   // per score instead of the 7 + 2 of the recompute pair (attention_tc.cu)
-  rc = attention_bwd_merged(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale, stream);
-  if (rc != 0) return rc < 0 ? rc : B200MM_OK;
-  rc = a3_launch_bwd<A3_MODE_DKV>(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, dsum, key_bias, dqkv, B, H, L, head_dim, scale, stream);
+  // (with dropout the mask is regenerated by the recompute pair; the merged kernel keeps the p = 0 arithmetic)
+  if (drop_p == 0.f) {
+    rc = attention_bwd_merged(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale, stream);
+    if (rc != 0) return rc < 0 ? rc : B200MM_OK;
+  }
+  rc = a3_launch_bwd<A3_MODE_DKV>(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, dsum, key_bias, dqkv, B, H, L, head_dim, scale, drop_p, drop_seed,
+                                  stream);
   if (rc) return rc;
-  return a3_launch_bwd<A3_MODE_DQ>(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, dsum, key_bias, dqkv, B, H, L, head_dim, scale, stream);
+  return a3_launch_bwd<A3_MODE_DQ>(qkv, ld, q_off, k_off, v_off, d_o, ldo, lse, dsum, key_bias, dqkv, B, H, L, head_dim, scale, drop_p, drop_seed,
+                                   stream);
 }
 
 }  // namespace b200mm
@@ -1257,22 +1327,37 @@ static int attn_check_common(const char* who, const void* qkv, int64_t ld, const
   return B200MM_OK;
 }
 
-extern "C" int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
-                                    const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, void* stream) {
+extern "C" int b200mm_attention_fwd_dropout(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo,
+                                            float* lse, const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale,
+                                            float drop_p, uint64_t drop_seed, void* stream) {
   int rc = attn_check_common("attention_fwd", qkv, ld, o, ldo, B, H, L, head_dim, q_off, k_off, v_off);
   if (rc) return rc;
   B200MM_REQUIRE(lse != nullptr, B200MM_ERR_SHAPE, "attention_fwd: lse is required");
-  return attention_fwd_v3(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, reinterpret_cast<cudaStream_t>(stream));
+  return attention_fwd_v3(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, drop_p, drop_seed,
+                          reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o,
-                                    int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H,
-                                    int32_t L, int32_t head_dim, float scale, void* stream) {
+extern "C" int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
+                                    const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, void* stream) {
+  return b200mm_attention_fwd_dropout(qkv, ld, q_off, k_off, v_off, o, ldo, lse, key_bias, B, H, L, head_dim, scale, 0.f, 0, stream);
+}
+
+extern "C" int b200mm_attention_bwd_dropout(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o,
+                                            const void* d_o, int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum,
+                                            int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, float drop_p, uint64_t drop_seed,
+                                            void* stream) {
   int rc = attn_check_common("attention_bwd", qkv, ld, o, ldo, B, H, L, head_dim, q_off, k_off, v_off);
   if (rc) return rc;
   B200MM_REQUIRE(lse && d_o && dqkv && dsum, B200MM_ERR_SHAPE, "attention_bwd: null pointer");
   B200MM_REQUIRE((reinterpret_cast<uintptr_t>(d_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, B200MM_ERR_ALIGN,
                  "attention_bwd: d_o/dqkv must be 16B aligned");
-  return attention_bwd_v3(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale,
+  return attention_bwd_v3(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale, drop_p, drop_seed,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o,
+                                    int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H,
+                                    int32_t L, int32_t head_dim, float scale, void* stream) {
+  return b200mm_attention_bwd_dropout(qkv, ld, q_off, k_off, v_off, o, d_o, ldo, lse, key_bias, dqkv, dsum, B, H, L, head_dim, scale, 0.f, 0,
+                                      stream);
 }

@@ -114,6 +114,37 @@ __device__ __forceinline__ float apply_dact(int act, float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// counter-based dropout: keep(seed, stream, index) is a pure function of its arguments (no RNG state), so the forward pass, the
+// backward pass and a recompute under checkpointing regenerate the same mask from the 64-bit seed alone. `stream` is the row of a
+// [rows, cols] activation or the (batch, head) item of an attention probability tensor; `index` the column / (query * L + key).
+// The mixer is the 32-bit finaliser "lowbias32" (two multiplies, three xor-shifts: 8 integer issue slots per decision, against
+// ~60 for Philox4x32-10 per 4 decisions); decisions are compared with a 32-bit threshold, so p is honoured to 2^-32.
+// Restated bit-exactly on the CPU in oracle/restated.py:dropout_keep (tests compare the masks).
+// Reference call sites: nn.Dropout in BertEmbeddings / BertSelfAttention / BertSelfOutput / BertOutput,
+// antmmf/modules/vision/backbone/clip/modeling_bert.py:84,124,158,180,232.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+// an element is DROPPED iff its hash is below the threshold
+static inline uint32_t drop_threshold(float p) {
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+}
+__host__ __device__ __forceinline__ uint32_t drop_stream_key(uint64_t seed, uint64_t stream) {
+  const uint32_t a = hash32(static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(stream) * 0x9E3779B9u));
+  return hash32(a + static_cast<uint32_t>(seed >> 32) + static_cast<uint32_t>(stream >> 32) * 0x85EBCA6Bu);
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t index, uint32_t thr) {
+  return hash32(key ^ (index * 0x9E3779B9u)) >= thr;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

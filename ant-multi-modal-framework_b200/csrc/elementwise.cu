@@ -28,6 +28,32 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ 
   }
 }
 
+// y[r, c] = keep(seed, r, c) ? x[r, c] * inv_keep : 0 — inverted dropout with the counter-based mask of common.cuh; one thread per
+// 8 consecutive columns of a row (one 16-byte access each way), the row key is hashed once per thread
+__global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy,
+                                                      int64_t rows, int32_t c8, uint32_t thr, float inv_keep, uint64_t seed) {
+  const int64_t total = rows * c8;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int64_t r = i / c8;
+    const uint32_t c = static_cast<uint32_t>(i - r * c8) * 8u;
+    const uint32_t key = drop_stream_key(seed, static_cast<uint64_t>(r));
+    float v[8];
+    unpack8e(*reinterpret_cast<const uint4*>(x + r * ldx + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = drop_keep(key, c + j, thr) ? v[j] * inv_keep : 0.f;
+    *reinterpret_cast<uint4*>(y + r * ldy + c) = pack8e(v);
+  }
+}
+
+// keep[b, h, q, k] = 1 iff the attention kernels keep probability (q, k) of item (b, h) under this seed (test / debugging aid)
+__global__ void __launch_bounds__(256) attention_dropout_mask_kernel(uint8_t* __restrict__ keep, int64_t items, int32_t L, uint32_t thr, uint64_t seed) {
+  const int64_t per = static_cast<int64_t>(L) * L, total = items * per;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int64_t item = i / per;
+    keep[i] = drop_keep(drop_stream_key(seed, static_cast<uint64_t>(item)), static_cast<uint32_t>(i - item * per), thr) ? 1 : 0;
+  }
+}
+
 // out[(row % period), col] += in[row, col]   (fp32 atomics; caller zero-fills out)
 //   period == 1 : bias gradient   db[n] = sum_m dY[m, n]
 //   period == L : positional-embedding gradient  dpos[l, :] = sum_b ds[b*L + l, :]
@@ -296,6 +322,26 @@ extern "C" int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, vo
   B200MM_REQUIRE(ALIGNED16(x) && ALIGNED16(y), B200MM_ERR_ALIGN, "act_fwd: pointers must be 16B aligned");
   act_fwd_kernel<<<grid_for(n / 8), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n / 8, act);
   return check_launch("act_fwd_kernel");
+}
+
+extern "C" int b200mm_dropout(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t cols, float p, uint64_t seed, void* stream) {
+  B200MM_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cols && ldy >= cols, B200MM_ERR_SHAPE,
+                 "dropout: rows=%lld cols=%d ldx=%lld ldy=%lld (cols and pitches must be multiples of 8)", (long long)rows, cols, (long long)ldx,
+                 (long long)ldy);
+  B200MM_REQUIRE(p >= 0.f && p < 1.f, B200MM_ERR_SHAPE, "dropout: p=%f must be in [0, 1)", p);
+  if (rows == 0) return B200MM_OK;
+  B200MM_REQUIRE(x && y && ALIGNED16(x) && ALIGNED16(y), B200MM_ERR_ALIGN, "dropout: pointers must be 16B aligned");
+  dropout_kernel<<<grid_for(rows * (cols / 8)), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                         ldy, rows, cols / 8, drop_threshold(p), 1.f / (1.f - p), seed);
+  return check_launch("dropout_kernel");
+}
+
+extern "C" int b200mm_attention_dropout_mask(uint8_t* keep, int32_t B, int32_t H, int32_t L, float drop_p, uint64_t drop_seed, void* stream) {
+  B200MM_REQUIRE(keep && B > 0 && H > 0 && L > 0 && L <= 65535 && drop_p >= 0.f && drop_p < 1.f, B200MM_ERR_SHAPE,
+                 "attention_dropout_mask: B=%d H=%d L=%d p=%f", B, H, L, drop_p);
+  const int64_t items = static_cast<int64_t>(B) * H;
+  attention_dropout_mask_kernel<<<grid_for(items * L * L), 256, 0, STREAM(stream)>>>(keep, items, L, drop_threshold(drop_p), drop_seed);
+  return check_launch("attention_dropout_mask_kernel");
 }
 
 extern "C" int b200mm_rowsum_periodic(const void* in, float* out, int64_t rows, int32_t W, int64_t period, void* stream) {

@@ -63,6 +63,9 @@ struct EpiParams {
   int64_t ld_dact;
   const __nv_bfloat16* residual;
   int64_t ldr;
+  uint32_t drop_thr;     // fused dropout (before the residual add): drop iff hash < drop_thr; 0 = off
+  float drop_inv_keep;   // 1 / (1 - p)
+  uint64_t drop_seed;
 };
 
 // epilogues of the contrastive-loss GEMMs (EPI_LSE / EPI_SOFTGRAD); z = alpha * <a_m, b_n> is the logit
@@ -136,6 +139,11 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = apply_act(e.act, v[j]);
   }
+  if (e.drop_thr != 0u) {
+    const uint32_t key = drop_stream_key(e.drop_seed, static_cast<uint64_t>(m));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = drop_keep(key, static_cast<uint32_t>(n) + j, e.drop_thr) ? v[j] * e.drop_inv_keep : 0.f;
+  }
   if (e.residual != nullptr) {
     uint4 r = *reinterpret_cast<const uint4*>(e.residual + m * e.ldr + n);
     float2 f0 = unpack_bf16x2(r.x), f1 = unpack_bf16x2(r.y), f2 = unpack_bf16x2(r.z), f3 = unpack_bf16x2(r.w);
@@ -154,19 +162,23 @@ __device__ __forceinline__ void epi_apply8(float (&v)[8], int64_t m, int64_t n, 
   }
 }
 
-// compile-time flavour encoding: bit0 bias, bit1 aux_out, bit2 residual, bit3 dact, bit4 f32 out, bit5 alpha != 1, bits 6-7 act
-__host__ __device__ constexpr int flavor_bits(bool bias, bool aux, bool res, bool dact, bool f32, bool scale, int act) {
-  return (bias ? 1 : 0) | (aux ? 2 : 0) | (res ? 4 : 0) | (dact ? 8 : 0) | (f32 ? 16 : 0) | (scale ? 32 : 0) | (act << 6);
+// compile-time flavour encoding: bit0 bias, bit1 aux_out, bit2 residual, bit3 dact, bit4 f32 out, bit5 alpha != 1, bits 6-7 act, bit8 dropout
+__host__ __device__ constexpr int flavor_bits(bool bias, bool aux, bool res, bool dact, bool f32, bool scale, int act, bool drop = false) {
+  return (bias ? 1 : 0) | (aux ? 2 : 0) | (res ? 4 : 0) | (dact ? 8 : 0) | (f32 ? 16 : 0) | (scale ? 32 : 0) | (act << 6) | (drop ? 256 : 0);
 }
 
 // Lean per-8-column epilogue for the GEMM warps: every address and flag is resolved by the caller once per tile / chunk;
 // here only arithmetic, one optional aux store and the output store remain.
 struct EpiFlags {
-  bool has_bias, has_aux, has_res, has_dact, f32, scale;
+  bool has_bias, has_aux, has_res, has_dact, f32, scale, drop;
   int act;
 };
+struct EpiDrop {  // dropout of this thread's 8 columns: the row's stream key, first column, threshold, 1 / (1 - p)
+  uint32_t key, col, thr;
+  float inv_keep;
+};
 __device__ __forceinline__ void epi_lean8(float (&v)[8], const EpiFlags& f, float alpha, const uint4& bias8, const uint4& ext8, void* dptr,
-                                          __nv_bfloat16* auxptr) {
+                                          __nv_bfloat16* auxptr, const EpiDrop& dr) {
   if (f.scale) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= alpha;
@@ -222,6 +234,10 @@ __device__ __forceinline__ void epi_lean8(float (&v)[8], const EpiFlags& f, floa
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
       }
+      if (f.drop) {  // dropout(dense(x)) BEFORE the residual joins (BertSelfOutput / BertOutput)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = drop_keep(dr.key, dr.col + j, dr.thr) ? v[j] * dr.inv_keep : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += x[j];
     }
@@ -232,6 +248,10 @@ __device__ __forceinline__ void epi_lean8(float (&v)[8], const EpiFlags& f, floa
     } else if (f.act == B200MM_ACT_GELU_ERF) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
+    }
+    if (f.drop) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = drop_keep(dr.key, dr.col + j, dr.thr) ? v[j] * dr.inv_keep : 0.f;
     }
   }
   if (f.f32) {
@@ -429,6 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __nv_bfloat16* aux0 = nullptr;  // aux_out shares D's pitch but is always bf16
       int64_t d_step = 0, ext_step = 0, aux_step = 0;
       uint32_t row_ok = 0;
+      uint32_t drop_key[4] = {0u, 0u, 0u, 0u};  // dropout stream keys of this lane's four rows
       uint4 nxt[4];
       const bool is_partial = (EPI == EPI_STD) && p.partial != nullptr;
       if constexpr (EPI == EPI_STD) {
@@ -436,12 +457,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (!is_partial) {
           fl.has_bias = p.epi.bias != nullptr; fl.has_aux = p.epi.aux_out != nullptr; fl.has_res = p.epi.residual != nullptr;
           fl.has_dact = p.epi.dact_in != nullptr; fl.f32 = p.epi.d_f32 != 0; fl.scale = p.epi.alpha != 1.f; fl.act = p.epi.act;
+          fl.drop = p.epi.drop_thr != 0u;
         } else {
           fl.f32 = true;
         }
         if constexpr (FL >= 0) {  // the host guarantees that the runtime arguments match the baked-in flavour
           fl.has_bias = (FL & 1) != 0; fl.has_aux = (FL & 2) != 0; fl.has_res = (FL & 4) != 0; fl.has_dact = (FL & 8) != 0;
-          fl.f32 = (FL & 16) != 0; fl.scale = (FL & 32) != 0; fl.act = (FL >> 6) & 3;
+          fl.f32 = (FL & 16) != 0; fl.scale = (FL & 32) != 0; fl.act = (FL >> 6) & 3; fl.drop = (FL & 256) != 0;
         }
         const __nv_bfloat16* ext = is_partial ? nullptr : (fl.has_dact ? p.epi.dact_in : p.epi.residual);
         const int64_t ld_ext = fl.has_dact ? p.epi.ld_dact : p.epi.ldr;
@@ -457,6 +479,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int it = 0; it < 4; ++it) {
           const int64_t mm = mm0 + it * 8;
           if (mm < p.M) row_ok |= 1u << it;
+          if (fl.drop) drop_key[it] = drop_stream_key(p.epi.drop_seed, static_cast<uint64_t>(mm));
           nxt[it] = make_uint4(0u, 0u, 0u, 0u);
           if (ext != nullptr && mm < p.M && n0 + cpart * 32 + cg < p.N) nxt[it] = *reinterpret_cast<const uint4*>(ext0 + it * ext_step + cpart * 32);
         }
@@ -508,7 +531,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   const float* srow = stage + (it * 8 + rr) * EPI_STAGE_PITCH + cg;
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] = srow[j];
-                  epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], d0 + it * d_step + c * 32 * esz, aux0 + it * aux_step + c * 32);
+                  const EpiDrop dr{drop_key[it], static_cast<uint32_t>(n0) + c * 32 + cg, p.epi.drop_thr, p.epi.drop_inv_keep};
+                  epi_lean8(v, fl, p.epi.alpha, bias8, cur[it], d0 + it * d_step + c * 32 * esz, aux0 + it * aux_step + c * 32, dr);
                 }
               }
             }
@@ -764,6 +788,8 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   B200MM_REQUIRE(!a->aux_out || (reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0, B200MM_ERR_ALIGN, "gemm: aux_out alignment");
   B200MM_REQUIRE(a->act >= 0 && a->act <= 2, B200MM_ERR_SHAPE, "gemm: unknown activation %d", a->act);
   B200MM_REQUIRE(!(a->dact_in && a->residual), B200MM_ERR_SHAPE, "gemm: dact_in and residual are mutually exclusive");
+  B200MM_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, B200MM_ERR_SHAPE, "gemm: drop_p=%f must be in [0, 1)", a->drop_p);
+  B200MM_REQUIRE(!(a->drop_p > 0.f && (a->dact_in || a->aux_out)), B200MM_ERR_SHAPE, "gemm: dropout cannot be combined with dact_in / aux_out");
 
   // CTA-pair (cta_group::2) kernels for everything that has at least one 256-row macro-tile per pair; B200MM_GEMM_CG=1 forces
   // the single-CTA kernels
@@ -801,6 +827,9 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   p.epi.ld_dact = a->ld_dact;
   p.epi.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.epi.ldr = a->ldr;
+  p.epi.drop_thr = a->drop_p > 0.f ? drop_threshold(a->drop_p) : 0u;
+  p.epi.drop_inv_keep = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.epi.drop_seed = a->drop_seed;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -816,7 +845,7 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
     // (and split-K partial tiles) runs the runtime-flag kernel
     const int fl = splits > 1 ? -1
                               : flavor_bits(a->bias != nullptr, a->aux_out != nullptr, a->residual != nullptr, a->dact_in != nullptr,
-                                            a->d_f32 != 0, a->alpha != 1.f, a->act);
+                                            a->d_f32 != 0, a->alpha != 1.f, a->act, p.epi.drop_thr != 0u);
     bool done = true;
 #define B200MM_TRY(AMN, BMN, ...)                                                                   \
   else if (a->a_mn == AMN && a->b_mn == BMN && fl == flavor_bits(__VA_ARGS__))                      \
@@ -825,6 +854,7 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
     //          bias   aux    res    dact   f32    scale  act
     B200MM_TRY(0, 0, true, false, false, false, false, false, B200MM_ACT_NONE)       // qkv / dense projections
     B200MM_TRY(0, 0, true, false, true, false, false, false, B200MM_ACT_NONE)        // out_proj / c_proj (+ residual)
+    B200MM_TRY(0, 0, true, false, true, false, false, false, B200MM_ACT_NONE, true)  // BERT self-output / output: dropout(dense) + residual
     B200MM_TRY(0, 0, true, true, false, false, false, false, B200MM_ACT_QUICKGELU)   // ViT c_fc
     B200MM_TRY(0, 0, true, true, false, false, false, false, B200MM_ACT_GELU_ERF)    // BERT intermediate
     B200MM_TRY(0, 0, false, false, false, false, false, false, B200MM_ACT_NONE)      // patch embedding

@@ -220,15 +220,25 @@ class ClsHeadFn(Function):
 # ======================================================================================================================
 # BERT layer (post-LN) — antmmf/modules/vision/backbone/clip/modeling_bert.py:253-270
 # ======================================================================================================================
-def _bert_layer_forward(x, p, key_bias, B, L, H, eps):
+def _drop_sites(drop):
+    """drop = None or (p_hidden, p_attn, seed_attn, seed_self_out, seed_out) -> the (p, seed) pairs of the three dropout sites of a BERT
+    layer: attention probabilities (modeling_bert.py:158), BertSelfOutput (:180), BertOutput (:232); None where p = 0."""
+    if drop is None:
+        return None, None, None
+    p_h, p_a, s_a, s_so, s_o = drop
+    return ((p_a, s_a) if p_a > 0 else None), ((p_h, s_so) if p_h > 0 else None), ((p_h, s_o) if p_h > 0 else None)
+
+
+def _bert_layer_forward(x, p, key_bias, B, L, H, eps, drop=None):
     (qkv_w, qkv_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b) = p
     Hd = x.shape[1]
+    d_attn, d_so, d_out = _drop_sites(drop)
     qkv = ops.gemm(x, qkv_w, bias=qkv_b)
-    c, lse = ops.attention_fwd(qkv, B, L, H, Hd // H, key_bias=key_bias)
-    s1 = ops.gemm(c, o_w, bias=o_b, residual=x)
+    c, lse = ops.attention_fwd(qkv, B, L, H, Hd // H, key_bias=key_bias, drop=d_attn)
+    s1 = ops.gemm(c, o_w, bias=o_b, residual=x, drop=d_so)  # dropout(dense(c)) + x in the epilogue
     x1, _, mean1, rstd1 = ops.layernorm_fwd(s1, ln1_w, ln1_b, eps)
     g, u = ops.gemm(x1, i_w, bias=i_b, act=ACT_GELU_ERF, aux_out=True)
-    s2 = ops.gemm(g, d_w, bias=d_b, residual=x1)
+    s2 = ops.gemm(g, d_w, bias=d_b, residual=x1, drop=d_out)
     del g, x1
     y, _, mean2, rstd2 = ops.layernorm_fwd(s2, ln2_w, ln2_b, eps)
     return y, (qkv, c, lse, s1, mean1, rstd1, u, s2, mean2, rstd2)
@@ -237,12 +247,13 @@ def _bert_layer_forward(x, p, key_bias, B, L, H, eps):
 class BertLayerFn(Function):
     @staticmethod
     def forward(ctx, x, q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b, key_bias, B, L, H,
-                eps, checkpoint):
+                eps, checkpoint, drop=None):
         qkv_w = torch.cat([q_w, k_w, v_w], dim=0)
         qkv_b = torch.cat([q_b, k_b, v_b], dim=0)
         p = (qkv_w, qkv_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b)
-        y, saved = _bert_layer_forward(x, p, key_bias, B, L, H, eps)
+        y, saved = _bert_layer_forward(x, p, key_bias, B, L, H, eps, drop)
         ctx.meta = (B, L, H, eps, checkpoint, key_bias is not None)
+        ctx.drop = drop  # probabilities + host-side seeds: the masks are regenerated, never stored
         kb = (key_bias,) if key_bias is not None else ()
         if checkpoint:
             ctx.save_for_backward(x, *p, *kb)
@@ -258,17 +269,21 @@ class BertLayerFn(Function):
         key_bias = t[13] if has_kb else None
         rest = t[13 + int(has_kb) :]
         (qkv_w, qkv_b, o_w, o_b, ln1_w, ln1_b, i_w, i_b, d_w, d_b, ln2_w, ln2_b) = p
+        d_attn, d_so, d_out = _drop_sites(ctx.drop)
         if checkpoint:
-            _, rest = _bert_layer_forward(x, p, key_bias, B, L, H, eps)
+            _, rest = _bert_layer_forward(x, p, key_bias, B, L, H, eps, ctx.drop)
         qkv, c, lse, s1, mean1, rstd1, u, s2, mean2, rstd2 = rest
         Hd = x.shape[1]
         I = i_w.shape[0]
         vg = _VecGrads(x.device, [3 * Hd, Hd, Hd, Hd, I, Hd, Hd, Hd])  # qkv_b | o_b | ln1 w,b | i_b | d_b | ln2 w,b
         ds2 = ops.layernorm_bwd(dy.contiguous(), s2, mean2, rstd2, ln2_w, vg[6], vg[7])
-        du, g = ops.gemm(ds2, d_w, b_mn=True, act=ACT_GELU_ERF, dact_in=u, aux_out=True)  # g = gelu(u) recomputed in the epilogue
-        d_d_w = _wgrad(ds2, g)
+        # gradient w.r.t. the dense output = the sum's gradient through the SAME mask; the residual branch keeps the unmasked ds2
+        dm2 = ops.dropout(ds2, *d_out) if d_out is not None else ds2
+        du, g = ops.gemm(dm2, d_w, b_mn=True, act=ACT_GELU_ERF, dact_in=u, aux_out=True)  # g = gelu(u) recomputed in the epilogue
+        d_d_w = _wgrad(dm2, g)
         del g
-        ops.rowsum_periodic(ds2, vg[5])
+        ops.rowsum_periodic(dm2, vg[5])
+        del dm2
         x1, _, _, _ = ops.layernorm_fwd(s1, ln1_w, ln1_b, eps)
         d_i_w = _wgrad(du, x1)
         del x1
@@ -277,10 +292,12 @@ class BertLayerFn(Function):
         del du, ds2
         ds1 = ops.layernorm_bwd(dx1, s1, mean1, rstd1, ln1_w, vg[2], vg[3])
         del dx1
-        d_o_w = _wgrad(ds1, c)
-        ops.rowsum_periodic(ds1, vg[1])
-        dc = ops.gemm(ds1, o_w, b_mn=True)
-        dqkv = ops.attention_bwd(qkv, c, dc, lse, B, L, H, Hd // H, key_bias=key_bias)
+        dm1 = ops.dropout(ds1, *d_so) if d_so is not None else ds1
+        d_o_w = _wgrad(dm1, c)
+        ops.rowsum_periodic(dm1, vg[1])
+        dc = ops.gemm(dm1, o_w, b_mn=True)
+        del dm1
+        dqkv = ops.attention_bwd(qkv, c, dc, lse, B, L, H, Hd // H, key_bias=key_bias, drop=d_attn)
         del dc
         d_qkv_w = _wgrad(dqkv, x)
         ops.rowsum_periodic(dqkv, vg[0])
@@ -289,7 +306,7 @@ class BertLayerFn(Function):
         dq_w, dk_w, dv_w = d_qkv_w[:Hd], d_qkv_w[Hd : 2 * Hd], d_qkv_w[2 * Hd :]
         dq_b, dk_b, dv_b = d_qkv_b[:Hd], d_qkv_b[Hd : 2 * Hd], d_qkv_b[2 * Hd :]
         return (dx, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_o_w, d_o_b, d_ln1_w, d_ln1_b, d_i_w, d_i_b, d_d_w, d_d_b, d_ln2_w, d_ln2_b,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 # ======================================================================================================================
@@ -297,9 +314,15 @@ class BertLayerFn(Function):
 # ======================================================================================================================
 class BertEmbeddingsFn(Function):
     @staticmethod
-    def forward(ctx, word_or_embeds, ids, pos_table, type_table, type_ids, ln_w, ln_b, L, eps, padding_idx, from_embeds):
+    def forward(ctx, word_or_embeds, ids, pos_table, type_table, type_ids, ln_w, ln_b, L, eps, padding_idx, from_embeds, drop=None):
         # from_embeds: word_or_embeds is [rows, H] (already embedded tokens), ids = arange(rows)
+        # drop = (p, seed): BertEmbeddings.dropout on the LayerNorm output (modeling_bert.py:101), in place
         y, s, mean, rstd = ops.embed_layernorm_fwd(word_or_embeds, ids, pos_table, L, type_table, type_ids, ln_w, ln_b, eps)
+        if drop is not None and drop[0] > 0:
+            ops.dropout(y, drop[0], drop[1], out=y)
+        else:
+            drop = None
+        ctx.drop = drop
         ctx.save_for_backward(s, mean, rstd, ln_w, ids, type_ids)
         ctx.meta = (L, padding_idx, from_embeds, word_or_embeds.shape[0], pos_table.shape[0], type_table.shape[0])
         return y
@@ -310,7 +333,10 @@ class BertEmbeddingsFn(Function):
         L, padding_idx, from_embeds, n_word, n_pos, n_type = ctx.meta
         Hd = s.shape[1]
         vg = _VecGrads(s.device, [Hd, Hd, n_pos * Hd, n_type * Hd])
-        ds = ops.layernorm_bwd(dy.contiguous(), s, mean, rstd, ln_w, vg[0], vg[1])
+        dy = dy.contiguous()
+        if ctx.drop is not None:
+            dy = ops.dropout(dy, ctx.drop[0], ctx.drop[1])
+        ds = ops.layernorm_bwd(dy, s, mean, rstd, ln_w, vg[0], vg[1])
         ops.rowsum_periodic(ds, vg[2].view(n_pos, Hd)[:L], period=L)
         ops.scatter_add_rows(ds, type_ids, vg[3].view(n_type, Hd))
         if from_embeds:
@@ -320,7 +346,7 @@ class BertEmbeddingsFn(Function):
             ops.scatter_add_rows(ds, ids, acc, skip_id=padding_idx if padding_idx is not None else -1)
             d_word = ops.cast_f32_bf16(acc)
         d_ln_w, d_ln_b, d_pos, d_type = vg.finish()
-        return d_word, None, d_pos.view(n_pos, Hd), d_type.view(n_type, Hd), None, d_ln_w, d_ln_b, None, None, None, None
+        return d_word, None, d_pos.view(n_pos, Hd), d_type.view(n_type, Hd), None, d_ln_w, d_ln_b, None, None, None, None, None
 
 
 # ======================================================================================================================

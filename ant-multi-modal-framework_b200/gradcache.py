@@ -9,7 +9,7 @@ keeps the FULL batch of negatives at micro-batch activation memory:
            (the all-gather / reduce-scatter of the fused contrastive kernels lives inside loss_fn, so the negatives are global)
   pass 2   for every micro-batch: re-encode with autograd, backward(embedding-gradient slice)  -> parameter gradients accumulate
 
-The result is the exact gradient of the full-batch loss (the towers are per-sample functions: no batch statistics, dropout p = 0),
+The result is the exact gradient of the full-batch loss (the towers are per-sample functions: no batch statistics; dropout masks are replayed in pass 2),
 at the price of one extra forward. The driver itself is tower-agnostic and runs on any device (CPU tests use toy towers); the B200
 path enters through the encoders and the loss handed to it.
 """
@@ -54,8 +54,20 @@ class GradCache:
             raise ValueError("GradCache: all towers must see the same number of samples")
         spans = _chunks(n, self.micro_batch)
         # pass 1: embeddings only
+        # (dropout: each micro-batch forward of pass 1 records the seed-sequence position it started from, pass 2 replays it, so both
+        # passes see the same masks — the counter-based analogue of GradCache's RNG-state snapshots)
+        from . import ops
+
+        drop_states = {}
         with torch.no_grad():
-            embs = [torch.cat([enc(x[s:e]) for s, e in spans]) for enc, x in zip(self.encoders, inputs)]
+            embs = []
+            for t, (enc, x) in enumerate(zip(self.encoders, inputs)):
+                outs = []
+                for s, e in spans:
+                    drop_states[(t, s)] = ops.get_dropout_state()
+                    outs.append(enc(x[s:e]))
+                embs.append(torch.cat(outs))
+        drop_end = ops.get_dropout_state()
         leaves = [e.detach().requires_grad_() for e in embs]
         # loss on the full batch; parameters used directly by the loss (logit_scale) get their gradient here
         with self._no_sync():
@@ -67,8 +79,10 @@ class GradCache:
         for i, (t, s, e) in enumerate(jobs):
             ctx = contextlib.nullcontext() if i == len(jobs) - 1 else self._no_sync()
             with ctx:
+                ops.set_dropout_state(drop_states[(t, s)])
                 out = self.encoders[t](inputs[t][s:e])
                 out.backward(d_embs[t][s:e].to(out.dtype))
+        ops.set_dropout_state(drop_end)
         return loss.detach()
 
 

@@ -5,11 +5,11 @@ post-LN, erf-GELU, no pooler) with the same config object, forward signatures, i
   encoder.layer.{i}.attention.self.{query,key,value}.*, .attention.output.{dense,LayerNorm}.*,
   .intermediate.dense.*, .output.{dense,LayerNorm}.*
 
-Dropout: the kernels implement p = 0 (eval-mode / parity semantics); a config with p > 0 is accepted and recorded,
-and a training-mode forward warns once that dropout is not applied (SURVEY.md §7 "Dropout parity").
+Dropout (modeling_bert.py:84,124,158,180,232): in training mode the three sites per layer (attention probabilities, self-output,
+output) and the embedding dropout run inside the kernels — fused into the attention softmax, the two projection-GEMM epilogues and one
+in-place pass — with counter-based masks regenerated from per-site 64-bit seeds in backward (`ops.next_dropout_seed`, re-based with
+`b200mm.ops.manual_seed`). Eval mode and p = 0 take the dropout-free kernels, bit-identical to before.
 """
-import warnings
-
 import torch
 from torch import nn
 
@@ -72,9 +72,10 @@ class BertEmbeddings(nn.Module):
             from_embeds = True
         if token_type_ids is None:
             token_type_ids = torch.zeros((B, L), dtype=torch.long, device=ids.device)
+        drop = (self.dropout.p, Fn.ops.next_dropout_seed()) if self.training and self.dropout.p > 0 else None
         y = Fn.BertEmbeddingsFn.apply(table, ids, _bf16(self.position_embeddings.weight), _bf16(self.token_type_embeddings.weight),
                                       token_type_ids.reshape(-1).contiguous(), _bf16(self.LayerNorm.weight), _bf16(self.LayerNorm.bias),
-                                      L, self.LayerNorm.eps, self.word_embeddings.padding_idx, from_embeds)
+                                      L, self.LayerNorm.eps, self.word_embeddings.padding_idx, from_embeds, drop)
         return y.view(B, L, -1)
 
 
@@ -114,6 +115,8 @@ class BertLayer(nn.Module):
         if config.hidden_act != "gelu":
             raise NotImplementedError(f"b200mm BertLayer: hidden_act={config.hidden_act!r}; the path uses erf-GELU ('gelu')")
         self.num_heads = config.num_attention_heads
+        self.hidden_dropout_prob = float(config.hidden_dropout_prob)
+        self.attention_probs_dropout_prob = float(config.attention_probs_dropout_prob)
         self.attention = _Attention(config)
         self.intermediate = _Intermediate(config)
         self.output = _SelfOutput(config, config.intermediate_size)
@@ -127,7 +130,11 @@ class BertLayer(nn.Module):
                                         o.dense.weight, o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias))
 
     def forward_tokens(self, x2d, key_bias, B, L):
-        return Fn.BertLayerFn.apply(x2d, *self.layer_params(), key_bias, B, L, self.num_heads, self.output.LayerNorm.eps, self.checkpoint)
+        drop = None
+        if self.training and (self.hidden_dropout_prob > 0 or self.attention_probs_dropout_prob > 0):
+            seeds = [Fn.ops.next_dropout_seed() for _ in range(3)]  # attention probabilities, self-output, output
+            drop = (self.hidden_dropout_prob, self.attention_probs_dropout_prob, *seeds)
+        return Fn.BertLayerFn.apply(x2d, *self.layer_params(), key_bias, B, L, self.num_heads, self.output.LayerNorm.eps, self.checkpoint, drop)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None):
         if head_mask is not None:
@@ -178,9 +185,6 @@ class BertEncoder(nn.Module):
         return outputs
 
 
-_warned_dropout = False
-
-
 class BertModel(nn.Module):
     """modeling_bert.py:421-534 (no pooler; returns (sequence_output, None, ...))."""
 
@@ -207,10 +211,6 @@ class BertModel(nn.Module):
             layer.checkpoint = enable
 
     def forward(self, input_ids, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None):
-        global _warned_dropout
-        if self.training and not _warned_dropout and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
-            warnings.warn("b200mm BertModel: dropout probabilities > 0 are not applied by the fused kernels (p = 0 semantics)")
-            _warned_dropout = True
         if head_mask is not None:
             raise NotImplementedError("b200mm BertModel: head_mask is not supported")
         if attention_mask is None:

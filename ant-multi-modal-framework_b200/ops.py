@@ -48,6 +48,43 @@ def _row_major_2d(t, name):
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# dropout seeds: every dropout site of a step draws one 64-bit seed = hash(base seed, running counter) on the HOST (no device RNG state,
+# no sync); the site keeps it for backward / recompute. `manual_seed` re-bases the sequence (default: torch.initial_seed() at first use).
+# ---------------------------------------------------------------------------------------------------------------------
+_DROP_BASE = None
+_DROP_COUNTER = 0
+
+
+def manual_seed(seed):
+    global _DROP_BASE, _DROP_COUNTER
+    _DROP_BASE, _DROP_COUNTER = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+
+
+def next_dropout_seed():
+    """A fresh 64-bit seed (splitmix64 of base + counter). Ranks of a data-parallel job decorrelate through their base seed."""
+    global _DROP_BASE, _DROP_COUNTER
+    if _DROP_BASE is None:
+        manual_seed(torch.initial_seed())
+    _DROP_COUNTER += 1
+    z = (_DROP_BASE + 0x9E3779B97F4A7C15 * _DROP_COUNTER) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def get_dropout_state():
+    """(base seed, counter) — with set_dropout_state the way to replay a forward pass with the same masks (GradCache pass 2)."""
+    if _DROP_BASE is None:
+        manual_seed(torch.initial_seed())
+    return _DROP_BASE, _DROP_COUNTER
+
+
+def set_dropout_state(state):
+    global _DROP_BASE, _DROP_COUNTER
+    _DROP_BASE, _DROP_COUNTER = state
+
+
 _SM = {}
 
 
@@ -77,11 +114,12 @@ def pick_splits(M, N, K, max_splits=32):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False, dact_in=None, residual=None, alpha=1.0,
-         out=None, out_f32=False, splits=None):
+         out=None, out_f32=False, splits=None, drop=None):
     """D = epilogue(alpha * A·B^T) on the tcgen05 GEMM (b200mm_gemm_bf16).
 
     a: [M, K] (a_mn=False) or [K, M] (a_mn=True, reduction index slow);  b: [N, K] (b_mn=False) or [K, N] (b_mn=True).
     Returns D [M, N] (bf16, or f32 if out_f32) — and the pre-activation copy if aux_out.
+    drop = (p, seed): inverted dropout on act(alpha*acc + bias) before the residual add, mask of `dropout(x, p, seed)`.
     """
     lib = _lib.load()
     lda = _row_major_2d(a, "a")
@@ -116,6 +154,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False
     if residual is not None:
         g.residual, g.ldr = residual.data_ptr(), _row_major_2d(residual, "residual")
     g.splits = splits
+    if drop is not None and drop[0] > 0.0:
+        g.drop_p, g.drop_seed = float(drop[0]), int(drop[1]) & 0xFFFFFFFFFFFFFFFF
     g.workspace = ws.data_ptr() if ws is not None else None
     g.workspace_bytes = ws_bytes
     prof = GEMM_PROFILE
@@ -225,8 +265,37 @@ def embed_layernorm_fwd(word, ids, pos, L, type_table, type_ids, w, b, eps):
     return y, s, mean, rstd
 
 
-def attention_fwd(qkv, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=None):
-    """qkv: [B*L, ld] fused projection; returns (o [B*L, H*hd], lse [B, H, L])."""
+def dropout(x, p, seed, out=None):
+    """y = x * keep(seed, row, col) / (1 - p) on a bf16 [rows, cols] matrix (counter-based mask: the same call on the gradient is the
+    backward pass; the GEMM epilogue with drop=(p, seed) yields the same mask). out may be x (in place)."""
+    lib = _lib.load()
+    ldx = _row_major_2d(x, "x")
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), device=x.device, dtype=BF16) if out is None else out
+    ldy = _row_major_2d(y, "out")
+    _lib.check(lib.b200mm_dropout(_ptr(x), ldx, _ptr(y), ldy, rows, cols, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "b200mm_dropout")
+    _count(1)
+    return y
+
+
+def attention_dropout_mask(B, H, L, p, seed, device="cuda"):
+    """bool [B, H, L, L]: which attention probabilities attention_fwd / attention_bwd keep under drop=(p, seed) (test / debugging aid)."""
+    lib = _lib.load()
+    keep = torch.empty((B, H, L, L), device=device, dtype=torch.uint8)
+    _lib.check(lib.b200mm_attention_dropout_mask(_ptr(keep), B, H, L, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+               "b200mm_attention_dropout_mask")
+    _count(1)
+    return keep.bool()
+
+
+def _drop_args(drop):
+    if drop is None or drop[0] <= 0.0:
+        return 0.0, 0
+    return float(drop[0]), int(drop[1]) & 0xFFFFFFFFFFFFFFFF
+
+
+def attention_fwd(qkv, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=None, drop=None):
+    """qkv: [B*L, ld] fused projection; returns (o [B*L, H*hd], lse [B, H, L]). drop = (p, seed): dropout on the probabilities."""
     lib = _lib.load()
     ld = _row_major_2d(qkv, "qkv")
     W = H * hd
@@ -236,15 +305,16 @@ def attention_fwd(qkv, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=No
     lse = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
     if key_bias is not None:
         _req(key_bias, "key_bias", torch.float32, 2)
+    dp, ds = _drop_args(drop)
     _lib.check(
-        lib.b200mm_attention_fwd(_ptr(qkv), ld, q_off, k_off, v_off, _ptr(o), W, _ptr(lse), _ptr(key_bias), B, H, L, hd,
-                                 1.0 / math.sqrt(hd), _stream()),
+        lib.b200mm_attention_fwd_dropout(_ptr(qkv), ld, q_off, k_off, v_off, _ptr(o), W, _ptr(lse), _ptr(key_bias), B, H, L, hd,
+                                         1.0 / math.sqrt(hd), dp, ds, _stream()),
         "b200mm_attention_fwd")
     _count(1)
     return o, lse
 
 
-def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=None):
+def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, q_off=0, k_off=None, v_off=None, drop=None):
     lib = _lib.load()
     ld = _row_major_2d(qkv, "qkv")
     W = H * hd
@@ -255,9 +325,10 @@ def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, q_off=0, k_off=N
         raise _lib.B200mmError("b200mm.attention_bwd: d_o must be contiguous")
     dqkv = torch.empty_like(qkv)
     dsum = torch.empty_like(lse)
+    dp, ds = _drop_args(drop)
     _lib.check(
-        lib.b200mm_attention_bwd(_ptr(qkv), ld, q_off, k_off, v_off, _ptr(o), _ptr(d_o), W, _ptr(lse), _ptr(key_bias), _ptr(dqkv),
-                                 _ptr(dsum), B, H, L, hd, 1.0 / math.sqrt(hd), _stream()),
+        lib.b200mm_attention_bwd_dropout(_ptr(qkv), ld, q_off, k_off, v_off, _ptr(o), _ptr(d_o), W, _ptr(lse), _ptr(key_bias), _ptr(dqkv),
+                                         _ptr(dsum), B, H, L, hd, 1.0 / math.sqrt(hd), dp, ds, _stream()),
         "b200mm_attention_bwd")
     _count(2)
     return dqkv

@@ -146,7 +146,7 @@ class _M2Step(torch.nn.Module):
         return self.m2.itc_loss(image, text, (text != 0).long(), group)
 
 
-def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0, image_res=0):
+def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0, image_res=0, dropout=0.0):
     from b200mm.modules import CNCLIP, CONFIGS, M2_CONFIGS, M2Encoder
 
     if name == "base_vtp-ViT-B-16":
@@ -180,8 +180,9 @@ def build_model(name, device, ckpt_every, keep_act=0, keep_ln=0, image_res=0):
     cfg = dict(CONFIGS[name])
     if image_res:
         cfg["image_resolution"] = image_res  # e.g. 336 for BASELINE.json configs[4]; positional embeddings are random-init at that size
-    cfg["text_hidden_dropout_prob"] = 0.0  # the fused kernels implement p = 0; stated in `config.dropout`
-    cfg["text_attention_probs_dropout_prob"] = 0.0
+    # the headline runs with p = 0 (same as the reference arm it is compared with); `--dropout 0.1` = the reference's training config
+    cfg["text_hidden_dropout_prob"] = dropout
+    cfg["text_attention_probs_dropout_prob"] = dropout
     torch.manual_seed(0)  # identical weights on every rank
     model = CNCLIP(**cfg)
     model = model.to(device).to(torch.bfloat16).train()
@@ -223,7 +224,7 @@ def run_ours(args):
     b200mm._lib.check(b200mm._lib.load().b200mm_check_device(), "b200mm_check_device")
 
     B, L = args.batch, args.seq_len
-    model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act, args.keep_ln, args.image_res)
+    model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act, args.keep_ln, args.image_res, args.dropout)
     res = cfg["image_resolution"]
     step_mod = TrainStep(model)
     if world > 1 and args.micro_batch == 0:
@@ -345,7 +346,7 @@ def run_ours(args):
                                     f"prj/M2_Encoder {args.model} (BEiT-3 multiway): infer_image + infer_text + symmetric ITC on both head pairs, fwd + bwd"),
                        "model": args.model, "per_gpu_batch": B, "global_batch": B * world, "image_res": res, "seq_len": L,
                        "parallelism": f"dp{world}" + (" + embedding all-gather / grad reduce-scatter, DDP grad all-reduce in the timed region" if world > 1 else ""),
-                       "dropout": 0.0, "recompute": f"GradCache two-pass, micro-batch {args.micro_batch} (second forward not counted)" if args.micro_batch else f"checkpoint every {args.ckpt_every} ViT block(s)" if args.ckpt_every else f"none (selective save: LN outputs recomputed in {max(0, cfg['vision_layers'] - args.keep_ln)} and the activated MLP hidden in {max(0, cfg['vision_layers'] - args.keep_act)} of {cfg['vision_layers']} ViT blocks)",
+                       "dropout": args.dropout, "recompute": f"GradCache two-pass, micro-batch {args.micro_batch} (second forward not counted)" if args.micro_batch else f"checkpoint every {args.ckpt_every} ViT block(s)" if args.ckpt_every else f"none (selective save: LN outputs recomputed in {max(0, cfg['vision_layers'] - args.keep_ln)} and the activated MLP hidden in {max(0, cfg['vision_layers'] - args.keep_act)} of {cfg['vision_layers']} ViT blocks)",
                        "l2_policy": "inputs and activations (>= 0.5 GB per tensor) exceed the 126 MB L2; no flush needed",
                        "loss": round(loss_val, 5), "peak_mem_gib": round(peak_mem, 1)},
             "e2e": {"value": round(e2e_val, 2), "unit": "pairs/s", "ms_per_step": round(e2e_ms, 3),
@@ -602,6 +603,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="pairs per GPU")
     ap.add_argument("--seq-len", type=int, default=77)
     ap.add_argument("--image-res", type=int, default=0, help="override the model's image resolution (336 = BASELINE.json configs[4])")
+    ap.add_argument("--dropout", type=float, default=0.0, help="BERT hidden / attention-probability dropout (the reference's CN-CLIP configs train with 0.1)")
     ap.add_argument("--ckpt-every", type=int, default=0, help="re-run every k-th ViT block in backward (0 = never)")
     ap.add_argument("--micro-batch", type=int, default=0, help="> 0: run the step through the GradCache two-pass driver with this micro-batch")
     ap.add_argument("--keep-act", type=int, default=0, help="ViT blocks that keep the activated MLP hidden instead of recomputing it (memory for time)")

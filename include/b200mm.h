@@ -78,6 +78,11 @@ typedef struct {
   int32_t splits;       /* >= 1 */
   void* workspace;      /* f32, needed iff splits > 1 */
   int64_t workspace_bytes;
+  /* fused dropout on act(alpha*acc + bias), BEFORE the residual add: the BertSelfOutput / BertOutput pattern
+   * LayerNorm(dropout(dense(x)) + input), clip/modeling_bert.py:176-184,228-236. Element (m, n) is kept iff
+   * b200mm_dropout's rule keeps (row m, column n) under the same seed, so backward masks dY with b200mm_dropout. 0 = off. */
+  float drop_p;
+  uint64_t drop_seed;
 } b200mm_gemm_args;
 
 int64_t b200mm_gemm_workspace_bytes(int64_t M, int64_t N, int32_t splits);
@@ -118,6 +123,19 @@ int b200mm_attention_fwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_o
 int b200mm_attention_bwd(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o,
                          int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H,
                          int32_t L, int32_t head_dim, float scale, void* stream);
+/* The same with dropout on the attention probabilities (BertSelfAttention: `attention_probs = self.dropout(attention_probs)`,
+ * clip/modeling_bert.py:124,158): P is normalised first, then element (b, h, query, key) is zeroed with probability drop_p and the
+ * survivors scaled by 1/(1-drop_p). The decision is the counter-based rule of b200mm_dropout with stream = b*H + h and
+ * index = query*L + key, regenerated (not stored) in backward from the same drop_seed. lse is that of the un-dropped softmax.
+ * drop_p = 0 is exactly b200mm_attention_fwd / _bwd. b200mm_attention_dropout_mask writes the decisions (1 = kept) as bytes [B, H, L, L]
+ * (test / debugging aid: the product path never materialises the mask). */
+int b200mm_attention_fwd_dropout(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, void* o, int64_t ldo, float* lse,
+                                 const float* key_bias, int32_t B, int32_t H, int32_t L, int32_t head_dim, float scale, float drop_p,
+                                 uint64_t drop_seed, void* stream);
+int b200mm_attention_bwd_dropout(const void* qkv, int64_t ld, int32_t q_off, int32_t k_off, int32_t v_off, const void* o, const void* d_o,
+                                 int64_t ldo, const float* lse, const float* key_bias, void* dqkv, float* dsum, int32_t B, int32_t H,
+                                 int32_t L, int32_t head_dim, float scale, float drop_p, uint64_t drop_seed, void* stream);
+int b200mm_attention_dropout_mask(uint8_t* keep, int32_t B, int32_t H, int32_t L, float drop_p, uint64_t drop_seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Contrastive similarity + log-softmax (tcgen05 GEMM with reduction epilogues).  z[m,n] = alpha * <a_m, b_n>.
@@ -189,6 +207,12 @@ int b200mm_mil_nce_matrix_bwd(const float* S, int64_t ld, const float* w, const 
  * q_cos/q_sin = cos/sin(l*inv_freq_i)*scale[l,i], k_cos/k_sin = the same with 1/scale. backward != 0 applies the transposed map. */
 int b200mm_xpos_apply(void* qkv, int64_t ld, int32_t q_off, int32_t k_off, const float* q_cos, const float* q_sin, const float* k_cos,
                       const float* k_sin, int64_t T, int32_t L, int32_t H, int32_t hd, int32_t backward, void* stream);
+/* Inverted dropout with a counter-based mask (nn.Dropout of the BERT tower: embeddings, self-output, output —
+ * clip/modeling_bert.py:84,101,180,232): y[r, c] = keep(seed, r, c) ? x[r, c] / (1 - p) : 0 on bf16 [rows, cols] (cols % 8 == 0, pitches
+ * ldx / ldy, y may alias x). keep() is a pure function of (seed, r, c) — hash32 / drop_stream_key / drop_keep in csrc/common.cuh,
+ * restated in oracle/restated.py:dropout_keep — so the backward pass applies the SAME call to the incoming gradient, and the fused
+ * GEMM epilogue (b200mm_gemm_args.drop_p) produces the identical mask for output element (m, n) = (r, c). */
+int b200mm_dropout(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t cols, float p, uint64_t seed, void* stream);
 /* y = act(x), bf16, n % 8 == 0 (activation recompute in backward: QuickGELU clip/model.py:222-224, erf-GELU modeling_bert.py:31-37) */
 int b200mm_act_fwd(const void* x, void* y, int64_t n, int32_t act, void* stream);
 /* out[(row % period), :] += in[row, :]  (f32 atomics, caller zero-fills): period 1 = bias gradient of nn.Linear,

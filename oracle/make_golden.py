@@ -9,6 +9,7 @@ Fixtures
   cnclip_tiny_h80.pt  same with vision_head_width=80-style odd head dim (width 160, 2 heads of 80) — ViT-H head geometry
   m2_tiny.pt       reference BEiT3 (multiway, 2 layers) + backbone_vl Encoder (1 layer) + ITC heads composed exactly as
                    VLMo.infer_image / infer_text (vlmo_module.py:323-405): hiddens, both feature pairs, ITC loss, all gradients
+  bert_dropout.pt  reference BertModel in training mode with dropout 0.1 / 0.2 and PRESET (counter-based) masks: output + all gradients
   losses.pt        get_mil_nce_loss / get_l1_simi_matrix / moco_loss known answers incl. SURVEY.md §8c (1)
 """
 import os
@@ -300,8 +301,66 @@ def make_stage2():
     print("stage2.pt", tuple(out["cross"]["logits"].shape), {k: float(v["loss"]) for k, v in out.items() if k.startswith("hard")})
 
 
+def make_bert_dropout(name="bert_dropout.pt", B=4, L=24, Hd=64, heads=2, layers=2, inter=128, vocab=300, p_hidden=0.1, p_attn=0.2, seed=77):
+    """The UNMODIFIED reference BertModel in TRAINING mode with dropout p > 0. torch.nn.functional.dropout (what nn.Dropout.forward calls) is
+    replaced for the duration of the forward by a function that applies y = x * keep / (1 - p) with PRESET masks, consumed in call order
+    (embeddings; then per layer: attention probabilities, self-output, output — modeling_bert.py:101,158,180,232). The masks are the
+    counter-based ones b200mm generates from its per-site seed sequence (b200mm.ops.manual_seed(seed) / next_dropout_seed), so the fixture pins
+    (a) where the oracle places each dropout and (b) what the B200 modules must produce from that seed."""
+    from b200mm import ops
+    from oracle import restated
+
+    ns = ref_loader.load()
+    cfg = ns.configuration_bert.BertConfig(vocab_size_or_config_json_file=vocab, hidden_size=Hd, num_hidden_layers=layers, num_attention_heads=heads,
+                                           intermediate_size=inter, hidden_dropout_prob=p_hidden, attention_probs_dropout_prob=p_attn,
+                                           max_position_embeddings=32, layer_norm_eps=1e-12)
+    torch.manual_seed(0)
+    model = ns.modeling_bert.BertModel(cfg)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p_ in model.named_parameters():
+            if n.endswith("bias") or "LayerNorm.weight" in n:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+    model.train()
+    gen = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, vocab, (B, L), generator=gen)
+    mask = torch.ones(B, L, dtype=torch.long)
+    mask[1, 17:] = 0
+    ids[1, 17:] = 0
+    ops.manual_seed(seed)
+    seeds = [ops.next_dropout_seed() for _ in range(1 + 3 * layers)]
+    calls = []
+
+    def preset_dropout(x, p=0.5, training=True, inplace=False):
+        i = len(calls)
+        if x.dim() == 4:   # attention probabilities [B, heads, L, L]
+            keep = restated.attention_dropout_keep(seeds[i], x.shape[0], x.shape[1], x.shape[2], p)
+        else:              # hidden states [B, L, H]
+            keep = restated.dropout_keep(seeds[i], x.shape[0] * x.shape[1], x.shape[2], p).view(x.shape)
+        calls.append((tuple(x.shape), p))
+        return x * keep.to(x.dtype) / (1.0 - p)
+
+    real = F.dropout
+    torch.nn.functional.dropout = preset_dropout
+    try:
+        out = model(ids, attention_mask=mask)[0]
+    finally:
+        torch.nn.functional.dropout = real
+    assert len(calls) == len(seeds), calls
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(123))
+    (out * probe).sum().backward()
+    fx = {"config": dict(vocab=vocab, hidden=Hd, heads=heads, layers=layers, inter=inter, p_hidden=p_hidden, p_attn=p_attn, seed=seed),
+          "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()}, "ids": ids, "mask": mask, "seeds": seeds, "calls": calls,
+          "probe": probe, "out": out.detach(), "grads": {n: p_.grad.detach().clone() for n, p_ in model.named_parameters() if p_.grad is not None}}
+    torch.save(fx, os.path.join(OUT, name))
+    print(name, "dropout calls", calls[:4], "...", "out norm", float(out.norm()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--bert-dropout-only" in sys.argv:
+        make_bert_dropout()
+        sys.exit(0)
     if "--stage2-only" in sys.argv:
         make_stage2()
         sys.exit(0)
@@ -328,3 +387,4 @@ if __name__ == "__main__":
     make_m2()
     make_m2("m2_tiny_xpos.pt", layers=1, vl_layers=1, L=11, B=4, xpos=True, max_source_positions=32)
     make_stage2()
+    make_bert_dropout()

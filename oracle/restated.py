@@ -37,9 +37,10 @@ def gelu_erf(x):
     return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def mha(q, k, v, heads, key_bias=None):
+def mha(q, k, v, heads, key_bias=None, prob_keep=None, p_drop=0.0):
     """softmax(q k^T / sqrt(hd) + key_bias) v per head; q,k,v [B, L, W]; key_bias [B, L] additive or None.
-    ViT: nn.MultiheadAttention inside clip/model.py:231,245-251 (no mask); BERT: modeling_bert.py:144-165."""
+    ViT: nn.MultiheadAttention inside clip/model.py:231,245-251 (no mask); BERT: modeling_bert.py:144-165.
+    prob_keep [B, heads, L, L] (bool) applies nn.Dropout(p_drop) to the probabilities with a GIVEN mask (modeling_bert.py:158)."""
     B, L, W = q.shape
     hd = W // heads
     qh = q.view(B, L, heads, hd).transpose(1, 2)
@@ -49,6 +50,8 @@ def mha(q, k, v, heads, key_bias=None):
     if key_bias is not None:
         s = s + key_bias[:, None, None, :]
     p = torch.softmax(s, dim=-1)
+    if prob_keep is not None:
+        p = p * prob_keep.to(p.dtype) / (1.0 - p_drop)
     return (p @ vh).transpose(1, 2).reshape(B, L, W)
 
 
@@ -95,44 +98,110 @@ def vit_forward(sd, image, heads, pfx="", n_layers=None):
 # ----------------------------------------------------------------------------------------------------------------
 # BERT  (clip/modeling_bert.py)
 # ----------------------------------------------------------------------------------------------------------------
-def bert_embeddings(sd, pfx, input_ids, token_type_ids=None, eps=1e-12, inputs_embeds=None):
-    """BertEmbeddings.forward, modeling_bert.py:86-103 (inputs_embeds variant: prj/base_vtp/.../clip_text_encoder.py:36-60)."""
+def _drop(x, keep, p_drop):
+    """nn.Dropout(p_drop) in training mode with a GIVEN keep mask (same shape as x, bool): x * keep / (1 - p)."""
+    return x if keep is None else x * keep.to(x.dtype) / (1.0 - p_drop)
+
+
+def bert_embeddings(sd, pfx, input_ids, token_type_ids=None, eps=1e-12, inputs_embeds=None, keep=None, p_drop=0.0):
+    """BertEmbeddings.forward, modeling_bert.py:86-103 (inputs_embeds variant: prj/base_vtp/.../clip_text_encoder.py:36-60);
+    `keep` = the mask of `self.dropout` on the LayerNorm output (:101)."""
     B, L = input_ids.shape if inputs_embeds is None else inputs_embeds.shape[:2]
     we = sd[pfx + "word_embeddings.weight"][input_ids] if inputs_embeds is None else inputs_embeds
     pe = sd[pfx + "position_embeddings.weight"][:L][None]
     tt = torch.zeros(B, L, dtype=torch.long) if token_type_ids is None else token_type_ids
     te = sd[pfx + "token_type_embeddings.weight"][tt]
-    return layer_norm(we + pe + te, sd[pfx + "LayerNorm.weight"], sd[pfx + "LayerNorm.bias"], eps)
+    return _drop(layer_norm(we + pe + te, sd[pfx + "LayerNorm.weight"], sd[pfx + "LayerNorm.bias"], eps), keep, p_drop)
 
 
-def bert_layer(sd, pfx, x, heads, key_bias, eps=1e-12):
-    """BertLayer.forward, modeling_bert.py:260-270 (post-LN)."""
+def bert_layer(sd, pfx, x, heads, key_bias, eps=1e-12, masks=None, p_hidden=0.0, p_attn=0.0):
+    """BertLayer.forward, modeling_bert.py:260-270 (post-LN). Training-mode dropout with GIVEN masks (the reference draws them from torch's
+    RNG; the oracle takes them as inputs so that a counter-based mask can be checked): masks = {"attn": [B, heads, L, L],
+    "self_out": [B, L, H], "out": [B, L, H]} for BertSelfAttention.dropout (:158), BertSelfOutput.dropout (:180), BertOutput.dropout (:232)."""
+    masks = masks or {}
     q = x @ sd[pfx + "attention.self.query.weight"].t() + sd[pfx + "attention.self.query.bias"]
     k = x @ sd[pfx + "attention.self.key.weight"].t() + sd[pfx + "attention.self.key.bias"]
     v = x @ sd[pfx + "attention.self.value.weight"].t() + sd[pfx + "attention.self.value.bias"]
-    c = mha(q, k, v, heads, key_bias)
-    a = c @ sd[pfx + "attention.output.dense.weight"].t() + sd[pfx + "attention.output.dense.bias"]
+    c = mha(q, k, v, heads, key_bias, masks.get("attn"), p_attn)
+    a = _drop(c @ sd[pfx + "attention.output.dense.weight"].t() + sd[pfx + "attention.output.dense.bias"], masks.get("self_out"), p_hidden)
     x1 = layer_norm(a + x, sd[pfx + "attention.output.LayerNorm.weight"], sd[pfx + "attention.output.LayerNorm.bias"], eps)
     i = gelu_erf(x1 @ sd[pfx + "intermediate.dense.weight"].t() + sd[pfx + "intermediate.dense.bias"])
-    o = i @ sd[pfx + "output.dense.weight"].t() + sd[pfx + "output.dense.bias"]
+    o = _drop(i @ sd[pfx + "output.dense.weight"].t() + sd[pfx + "output.dense.bias"], masks.get("out"), p_hidden)
     return layer_norm(o + x1, sd[pfx + "output.LayerNorm.weight"], sd[pfx + "output.LayerNorm.bias"], eps)
 
 
-def bert_encoder(sd, pfx, x, heads, attention_mask, eps=1e-12, n_layers=None):
+def bert_encoder(sd, pfx, x, heads, attention_mask, eps=1e-12, n_layers=None, masks=None, p_hidden=0.0, p_attn=0.0):
     """BertEncoder.forward (modeling_bert.py:283-314) with the additive mask of BertModel.forward (:487-497):
     (1 - mask) * -10000 on the key axis."""
     key_bias = (1.0 - attention_mask.to(x.dtype)) * -10000.0
     if n_layers is None:
         n_layers = 1 + max(int(k[len(pfx) :].split(".")[1]) for k in sd if k.startswith(pfx + "layer."))
     for i in range(n_layers):
-        x = bert_layer(sd, f"{pfx}layer.{i}.", x, heads, key_bias, eps)
+        x = bert_layer(sd, f"{pfx}layer.{i}.", x, heads, key_bias, eps, masks[i] if masks else None, p_hidden, p_attn)
     return x
 
 
-def bert_forward(sd, input_ids, attention_mask, heads, pfx="", eps=1e-12):
-    """BertModel.forward, modeling_bert.py:469-534. Returns sequence_output [B, L, H]."""
-    x = bert_embeddings(sd, pfx + "embeddings.", input_ids, eps=eps)
-    return bert_encoder(sd, pfx + "encoder.", x, heads, attention_mask, eps)
+def bert_forward(sd, input_ids, attention_mask, heads, pfx="", eps=1e-12, masks=None, p_hidden=0.0, p_attn=0.0):
+    """BertModel.forward, modeling_bert.py:469-534. Returns sequence_output [B, L, H]. masks = {"emb": [B, L, H], "layers": [per-layer dict]}
+    switches the training-mode dropouts on with given masks (see bert_layer)."""
+    masks = masks or {}
+    x = bert_embeddings(sd, pfx + "embeddings.", input_ids, eps=eps, keep=masks.get("emb"), p_drop=p_hidden)
+    return bert_encoder(sd, pfx + "encoder.", x, heads, attention_mask, eps, masks=masks.get("layers"), p_hidden=p_hidden, p_attn=p_attn)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# counter-based dropout masks — CPU restatement of hash32 / drop_stream_key / drop_keep (csrc/common.cuh), bit-exact.
+# The reference's nn.Dropout draws from torch's stateful RNG (modeling_bert.py:84,124,158,180,232); b200mm replaces the generator, not
+# the arithmetic: y = x * keep / (1 - p). The tests feed the SAME masks to this oracle and compare everything downstream.
+# ----------------------------------------------------------------------------------------------------------------
+def _hash32(x):
+    import numpy as np
+
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def _stream_key(seed, stream):
+    import numpy as np
+
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    stream = stream.astype(np.uint64)
+    lo = (stream & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hi = (stream >> np.uint64(32)).astype(np.uint32)
+    a = _hash32(np.uint32(seed & 0xFFFFFFFF) ^ (lo * np.uint32(0x9E3779B9)))
+    return _hash32(a + np.uint32(seed >> 32) + hi * np.uint32(0x85EBCA6B))
+
+
+def drop_threshold(p):
+    t = float(torch.tensor(p, dtype=torch.float32)) * 4294967296.0  # the C side receives p as a float
+    return 4294967295 if t >= 4294967295.0 else int(t)
+
+
+def dropout_keep(seed, rows, cols, p, row0=0):
+    """keep[r, c] of b200mm_dropout / the GEMM epilogue for rows row0 .. row0+rows-1: stream = row, index = column. bool [rows, cols]."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        key = _stream_key(seed, np.arange(row0, row0 + rows, dtype=np.uint64))[:, None]
+        idx = np.arange(cols, dtype=np.uint32)[None, :] * np.uint32(0x9E3779B9)
+        keep = _hash32(key ^ idx) >= np.uint32(drop_threshold(p))
+    return torch.from_numpy(keep)
+
+
+def attention_dropout_keep(seed, B, H, L, p):
+    """keep[b, h, q, k] of the attention kernels: stream = b * H + h, index = q * L + k. bool [B, H, L, L]."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        key = _stream_key(seed, np.arange(B * H, dtype=np.uint64))[:, None]
+        idx = np.arange(L * L, dtype=np.uint32)[None, :] * np.uint32(0x9E3779B9)
+        keep = _hash32(key ^ idx) >= np.uint32(drop_threshold(p))
+    return torch.from_numpy(keep).view(B, H, L, L)
 
 
 # ----------------------------------------------------------------------------------------------------------------

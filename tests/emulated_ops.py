@@ -24,8 +24,22 @@ def _dact(act, x):
     return g
 
 
+def _keep(rows, cols, p, seed):
+    from oracle import restated
+
+    return restated.dropout_keep(seed, rows, cols, p)
+
+
+def dropout(x, p, seed, out=None):
+    y = (x.float() * _keep(x.shape[0], x.shape[1], p, seed) / (1.0 - p)).to(BF)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False, dact_in=None, residual=None, alpha=1.0, out=None,
-         out_f32=False, splits=None):
+         out_f32=False, splits=None, drop=None):
     A = a.float().t() if a_mn else a.float()
     Bm = b.float() if b_mn else b.float().t()
     d = alpha * (A @ Bm)
@@ -38,6 +52,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, aux_out=False
     else:
         aux = d.to(BF)
         d = _act(act, d)
+    if drop is not None and drop[0] > 0:
+        d = d * _keep(d.shape[0], d.shape[1], drop[0], drop[1]) / (1.0 - drop[0])
     if residual is not None:
         d = d + residual.float()
     d = d if out_f32 else d.to(BF)
@@ -106,24 +122,29 @@ def embed_layernorm_fwd(word, ids, pos, L, type_table, type_ids, w, b, eps):
     return y, s, mean, rstd
 
 
-def _attn(qkv, B, L, H, hd, key_bias):
+def _attn(qkv, B, L, H, hd, key_bias, drop=None):
     W = H * hd
     q, k, v = (qkv[:, i * W:(i + 1) * W].reshape(B, L, H, hd).transpose(1, 2) for i in range(3))
     s = q @ k.transpose(-1, -2) / math.sqrt(hd)
     if key_bias is not None:
         s = s + key_bias[:, None, None, :]
-    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, W), torch.logsumexp(s, -1)
+    pr = torch.softmax(s, -1)
+    if drop is not None and drop[0] > 0:
+        from oracle import restated
+
+        pr = pr * restated.attention_dropout_keep(drop[1], B, H, L, drop[0]) / (1.0 - drop[0])
+    return (pr @ v).transpose(1, 2).reshape(B * L, W), torch.logsumexp(s, -1)
 
 
-def attention_fwd(qkv, B, L, H, hd, key_bias=None, **kw):
-    o, lse = _attn(qkv.float(), B, L, H, hd, key_bias)
+def attention_fwd(qkv, B, L, H, hd, key_bias=None, drop=None, **kw):
+    o, lse = _attn(qkv.float(), B, L, H, hd, key_bias, drop)
     return o.to(BF), lse
 
 
-def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, **kw):
+def attention_bwd(qkv, o, d_o, lse, B, L, H, hd, key_bias=None, drop=None, **kw):
     with torch.enable_grad():
         x = qkv.float().detach().requires_grad_()
-        out, _ = _attn(x, B, L, H, hd, key_bias)
+        out, _ = _attn(x, B, L, H, hd, key_bias, drop)
         (g,) = torch.autograd.grad(out, x, d_o.float())
     return g.to(BF)
 

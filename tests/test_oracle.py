@@ -245,3 +245,34 @@ def test_restated_m2_fused_input_matches_golden(golden_dir, name):
     # both experts of the backbone layers are exercised, the vl encoder and the heads are not
     assert "backbone.encoder.layers.0.ffn.A.fc1.weight" in fx["fused_grads"] and "backbone.encoder.layers.0.ffn.B.fc1.weight" in fx["fused_grads"]
     assert not any(k.startswith(("backbone_vl.", "itc_")) for k in fx["fused_grads"])
+
+
+def test_restated_bert_dropout_matches_reference_with_preset_masks(golden_dir):
+    """Training-mode dropout: tests/golden/bert_dropout.pt holds the UNMODIFIED reference BertModel run with F.dropout replaced by preset
+    masks (make_golden.make_bert_dropout). The oracle, given the masks its restated hash generates from the recorded seeds, must reproduce the
+    output and every gradient — this pins WHERE each dropout sits (modeling_bert.py:101,158,180,232) and the y = x keep / (1 - p) rule."""
+    fx = torch.load(os.path.join(golden_dir, "bert_dropout.pt"), weights_only=False)
+    c = fx["config"]
+    B, L = fx["ids"].shape
+    seeds = fx["seeds"]
+    masks = {"emb": restated.dropout_keep(seeds[0], B * L, c["hidden"], c["p_hidden"]).view(B, L, c["hidden"]), "layers": []}
+    for i in range(c["layers"]):
+        s_a, s_so, s_o = seeds[1 + 3 * i: 4 + 3 * i]
+        masks["layers"].append({"attn": restated.attention_dropout_keep(s_a, B, c["heads"], L, c["p_attn"]),
+                                "self_out": restated.dropout_keep(s_so, B * L, c["hidden"], c["p_hidden"]).view(B, L, c["hidden"]),
+                                "out": restated.dropout_keep(s_o, B * L, c["hidden"], c["p_hidden"]).view(B, L, c["hidden"])})
+    # the call order the reference made: embeddings, then (probabilities, self-output, output) per layer
+    assert [len(sh) for sh, _ in fx["calls"]] == [3] + [4, 3, 3] * c["layers"]
+    sd = {k: v.clone().requires_grad_(torch.is_floating_point(v)) for k, v in fx["state_dict"].items()}
+    out = restated.bert_forward(sd, fx["ids"], fx["mask"], c["heads"], masks=masks, p_hidden=c["p_hidden"], p_attn=c["p_attn"])
+    torch.testing.assert_close(out, fx["out"], rtol=1e-4, atol=1e-5)
+    (out * fx["probe"]).sum().backward()
+    for n, g in fx["grads"].items():
+        got = sd[n].grad
+        if n == "embeddings.word_embeddings.weight":  # nn.Embedding(padding_idx=0): the reference gives row 0 no gradient (modeling_bert.py:71-73)
+            assert float(g[0].abs().max()) == 0.0
+            got, g = got[1:], g[1:]
+        torch.testing.assert_close(got, g, rtol=2e-3, atol=1e-5, msg=lambda m, n=n: f"{n}: {m}")
+    # without the masks the output differs (the fixture really ran with dropout on)
+    plain = restated.bert_forward({k: v.detach() for k, v in sd.items()}, fx["ids"], fx["mask"], c["heads"])
+    assert float((plain - fx["out"]).abs().max()) > 0.1
