@@ -227,7 +227,7 @@ def run_ours(args):
     model, cfg = build_model(args.model, device, args.ckpt_every, args.keep_act, args.keep_ln, args.image_res, args.dropout)
     res = cfg["image_resolution"]
     step_mod = TrainStep(model)
-    if world > 1 and args.micro_batch == 0:
+    if world > 1 and args.micro_batch == 0 and args.grad_sync == "ddp":
         step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                              static_graph=True)
     image_h, text_h = synth_batch(B * cfg.get("frames", 1), res, L, cfg["vocab_size"], 1234 + rank)
@@ -244,6 +244,12 @@ def run_ours(args):
             return cnclip_gradcache_step(model, img, txt, args.micro_batch)
         loss = step_mod(img, txt)
         loss.backward()
+        if world > 1 and args.grad_sync == "flat":
+            # A/B against DDP's bucketed overlap: the parameter gradients averaged in flat buckets AFTER backward (nothing shares the SMs
+            # with the GEMMs; the all-reduce is exposed instead)
+            from b200mm.gradcache import allreduce_grads
+
+            allreduce_grads(list(model.parameters()))
         return loss
 
     def barrier():
@@ -287,7 +293,8 @@ def run_ours(args):
         loss = step(image_d, text_d)
     e1.record()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_rank = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_rank)
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.LAUNCHES
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
@@ -302,6 +309,14 @@ def run_ours(args):
     gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
     dominant = dominant_launch(prof, peak_tf) if rank == 0 else None
+    per_rank = None
+    if world > 1:
+        # where the weak-scaling loss comes from: every rank's own step time and GEMM rate (the reported step is the slowest rank's)
+        t = torch.tensor([ms_rank / args.steps, gemm_tf, gemm_ms / args.steps], device=device, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = {"ms_per_step": [round(float(x[0]), 2) for x in allt], "gemm_tflops": [round(float(x[1]), 1) for x in allt],
+                    "gemm_ms_per_step": [round(float(x[2]), 2) for x in allt], "grad_sync": args.grad_sync}
 
     if args.profile and rank == 0:
         write_profile(args, prof, step, image_d, text_d, B)
@@ -359,6 +374,8 @@ def run_ours(args):
                          "traffic": dominant.get("traffic") if dominant else None, "dominant_launch": dominant,
                          "whole_step_frac": round(pairs_per_s / world * fpp / 1e12 / peak_tf, 4) if fpp else None},
         }
+        if per_rank is not None:
+            out["per_rank"] = per_rank
         headline = args.model in FLOP_PER_PAIR and not args.model.startswith(("M2", "base_vtp"))
         if world == 1 and not args.no_gpu_baseline and headline and not args.image_res:
             del step_mod, model
@@ -604,6 +621,7 @@ def main():
     ap.add_argument("--seq-len", type=int, default=77)
     ap.add_argument("--image-res", type=int, default=0, help="override the model's image resolution (336 = BASELINE.json configs[4])")
     ap.add_argument("--dropout", type=float, default=0.0, help="BERT hidden / attention-probability dropout (the reference's CN-CLIP configs train with 0.1)")
+    ap.add_argument("--grad-sync", default="ddp", choices=["ddp", "flat"], help="N > 1: DDP's bucketed all-reduce overlapped with backward, or flat buckets after backward")
     ap.add_argument("--ckpt-every", type=int, default=0, help="re-run every k-th ViT block in backward (0 = never)")
     ap.add_argument("--micro-batch", type=int, default=0, help="> 0: run the step through the GradCache two-pass driver with this micro-batch")
     ap.add_argument("--keep-act", type=int, default=0, help="ViT blocks that keep the activated MLP hidden instead of recomputing it (memory for time)")

@@ -21,11 +21,14 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# measured on B200 (profiles/parity_r02.md): the asserted bound = 1.5 x measured
-BOUND_FEATURES = 1.5 * 1.0e-2
-BOUND_LOSS_ABS = 1.5 * 1.0e-2
-BOUND_GRAD_MEDIAN = 1.5 * 2.0e-2
-BOUND_GRAD_WORST_VS_EAGER = 1.5
+# measured on B200 (profiles/parity_r02.md; ours / eager-bf16 calibrator): features 1.14e-2 / 1.54e-2 (image), 1.16e-2 / 1.40e-2 (text);
+# |loss - oracle| 5.4e-4 / 2.1e-4; gradient rel-L2 median 0.103 / 0.116, p90 0.177 / 0.193, worst ratio ours / eager 1.37 (a LayerNorm bias).
+# The gradients of a random-init 24 + 12-layer model at B = 4 are ill-conditioned (the eager-bf16 reference arithmetic is 11.6 % from fp32),
+# so they are bounded both absolutely (1.5 x measured) and against the calibrator.
+BOUND_FEATURES = 1.5 * 1.16e-2
+BOUND_LOSS_ABS = 1.5e-3
+BOUND_GRAD_MEDIAN = 1.5 * 0.103
+BOUND_GRAD_WORST_VS_EAGER = 2.0
 
 
 def rel_l2(got, ref):
@@ -112,6 +115,6 @@ def test_vit_l14_bert_base_full_depth_vs_oracle():
     for k, (mine, eag) in feats.items():
         assert mine < BOUND_FEATURES, (k, mine, eag)
     assert loss_err[0] < BOUND_LOSS_ABS * max(1.0, abs(float(o_loss))), loss_err
-    assert med < max(BOUND_GRAD_MEDIAN, BOUND_GRAD_WORST_VS_EAGER * med_e), (med, med_e)
+    assert med < BOUND_GRAD_MEDIAN and med < 1.5 * med_e, (med, med_e)
     for n in ours:
-        assert ours[n] < max(BOUND_GRAD_MEDIAN, BOUND_GRAD_WORST_VS_EAGER * eager[n]), (n, ours[n], eager[n])
+        assert ours[n] < BOUND_GRAD_WORST_VS_EAGER * max(eager[n], med_e), (n, ours[n], eager[n])
