@@ -56,6 +56,11 @@ SIGNATURES = {
     "b200mm_contrast_lse_partials": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P]),
     "b200mm_contrast_lse_merge": (c_int32, [_P, _P, c_int32, _P, _P, c_int32, _P, c_int32, _P, _P, c_int64, _P]),
     "b200mm_contrast_softgrad": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, _P, c_float, c_float, c_int32, _P, c_int64, _P, _P]),
+    "b200mm_contrast_lse_partials_pair": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_float, _P, c_int64,
+                                                    _P, _P, _P, _P, _P, _P, _P]),
+    "b200mm_contrast_softgrad_pair": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, _P,
+                                                c_int64, _P, _P, _P, _P, c_float, _P, c_float, c_int32, c_int32, c_int32, c_int32, _P, _P, c_int64,
+                                                _P, _P]),
     "b200mm_contrast_rank": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P]),
     "b200mm_masked_mean_fwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "b200mm_masked_mean_bwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),

@@ -14,6 +14,8 @@ Loss scaling under data parallelism: a rank returns W * (its share of the global
 the global loss and DDP's gradient averaging yields exactly the gradient of the global loss — the same result as the
 reference, where every rank evaluates the full B_g x B_g loss on gathered embeddings.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch.autograd import Function
@@ -129,6 +131,94 @@ class _ContrastiveFn(Function):
         return da.to(BF16), db.to(BF16), d_ls, None, None
 
 
+def _gather_vec(v, group):
+    """f32 [n] of every rank -> [world, n] (rank order)."""
+    rank, world = _world(group)
+    if world == 1:
+        return v.reshape(1, -1)
+    out = torch.empty(world * v.numel(), device=v.device, dtype=v.dtype)
+    dist.all_gather_into_tensor(out, v.contiguous(), group=group)
+    return out.view(world, v.numel())
+
+
+class _ContrastiveTwoSidedFn(Function):
+    """The same two losses as _ContrastiveFn (same arguments, same value), restructured — the OPT-IN backend "two_sided"
+    (set_backend / B200MM_CONTRASTIVE): written at the end of round 2 after the round's GPU budget was spent, verified on the CPU against
+    the oracle over the emulated kernels (tests/test_contrastive_two_sided_cpu.py) but NOT yet run on hardware; its GPU checks are
+    tests/test_zz_contrastive_two_sided_gpu.py (expected-to-pass, non-strict). The default stays the hardware-verified _ContrastiveFn.
+
+    Per step and rank: ONE all-gather of the embeddings ([B, 2E] rows) and one of the row log-sum-exps (2 B floats); no gradient exchange.
+    Every logit z[i, t] = s <a_i, b_t> is an entry of block A on the rank that owns row i AND of block Bt on the rank that owns row t; with the
+    row LSEs of all ranks at hand a rank evaluates both softmax terms of its own rows' logits at once (two-sided gradient tiles), so
+        d a_i = sum_t G[i, t] b_t,   G = coef s (e^{z - lseA_i} + e^{z - lseB_t} - 2 [t = i])          ('clip'; 'mil' drops the excluded diagonal terms)
+    is the complete gradient of the global loss — what GradientAllGather.backward's reduce-scatter (distributed_utils.py:104-116) assembles
+    from every rank's partial products in the reference. This needs the upstream gradient to be the same on every rank, which data-parallel
+    training guarantees (each rank calls backward on its own loss with gradient 1 or the same loss scale).
+    Neither exp(log_scale) nor the upstream gradient is read by the host: both reach the kernels as device scalars."""
+
+    @staticmethod
+    def forward(ctx, a, b, log_scale, mode, group):
+        rank, world = _world(group)
+        B, E = a.shape
+        if mode not in ("clip", "mil"):
+            raise ValueError(f"unknown contrastive mode {mode!r}")
+        alpha_dev = torch.exp(log_scale.detach().float()).reshape(1) if log_scale is not None else None
+        # both modalities travel as [B, 2E] rows; the two gathered matrices are column views of the same buffer (row pitch 2E), which the
+        # TMA descriptors of the kernels take as they are
+        if world > 1:
+            ab_all, Bg = _gather_rows(torch.cat([a, b], dim=1), group)
+            a_all, b_all = ab_all[:, :E], ab_all[:, E:]
+        else:
+            a_all, Bg = _gather_rows(a, group)
+            b_all, _ = _gather_rows(b, group)
+        off = rank * B
+        # rows a_loc x all b   and   rows b_loc x all a, one grouped launch
+        partsA, partsB = ops.contrast_lse_partials_pair(a, b_all[:Bg], b, a_all[:Bg], 1.0, off, alpha_dev=alpha_dev)
+        loss_sum = torch.zeros(1, device=a.device, dtype=torch.float32)
+        if mode == "clip":
+            lseA = ops.contrast_lse_merge(partsA[:2], None, partsA[2], False, loss_sum)
+            lseB = ops.contrast_lse_merge(partsB[:2], None, partsB[2], False, loss_sum)
+            denom = 2.0 * Bg
+            lse_all = _gather_vec(torch.cat([lseA, lseB]), group)                       # [world, 2B]
+            lseA_all, lseB_all = lse_all[:, :B].reshape(-1), lse_all[:, B:].reshape(-1)   # [Bg] each, rank order = row order
+        else:
+            lseA = ops.contrast_lse_merge(partsA[:2], partsB[:2], partsA[2], True, loss_sum)
+            lseB = lseA
+            denom = float(Bg)
+            lseA_all = lseB_all = _gather_vec(lseA, group).reshape(-1)
+        ctx.save_for_backward(a, b, a_all, b_all, lseA, lseB, lseA_all.contiguous(), lseB_all.contiguous(), alpha_dev)
+        ctx.meta = (mode, off, Bg, denom, world, log_scale.dtype if log_scale is not None else None)
+        # W * local share: mean over ranks == global loss (see module docstring)
+        return (loss_sum * (world / denom)).reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, a_all, b_all, lseA, lseB, lseA_all, lseB_all, alpha_dev = ctx.saved_tensors
+        mode, off, Bg, denom, world, scale_dtype = ctx.meta
+        has_scale = scale_dtype is not None
+        dscale = torch.zeros(1, device=a.device, dtype=torch.float32) if has_scale else None
+        coef_dev = gout.detach().float().reshape(1).contiguous()
+        if mode == "clip":
+            flags, dsub = (0, 0, 0, 0), 2.0
+        else:
+            # union row of MIL-NCE: the positive appears once (in A, dsub 1); Bt's diagonal is excluded — as a column term for the video
+            # rows (problem 0), as a row term for the text rows (problem 1)
+            flags, dsub = (0, 1, 1, 0), 1.0
+        # problem 0: rows a_loc (row LSE lseA) against all b (their rows' LSE in Bt: lseB_all); problem 1: rows b_loc against all a
+        GA, GB = ops.contrast_softgrad_pair(a, b_all, b, a_all, Bg, 1.0, off, lseA, lseB_all, lseB, lseA_all, world / denom, dsub, flags,
+                                            dscale, alpha_dev=alpha_dev, coef_dev=coef_dev)
+        # complete row gradients (B operand read MN-major: [K = Bg_pad, N = E]); no gradient leaves the rank. The tiles leave the positive's
+        # -dsub term out: it is the one large entry of a row, and it is added here in fp32 instead of being rounded to bf16 inside G
+        # ([B, E] parameter-sized ops on device scalars, no host read)
+        dcoef = coef_dev * (-dsub * world / denom)
+        if alpha_dev is not None:
+            dcoef = dcoef * alpha_dev
+        da = torch.addcmul(ops.gemm(GA, b_all, b_mn=True, out_f32=True), b.float(), dcoef)
+        db = torch.addcmul(ops.gemm(GB, a_all, b_mn=True, out_f32=True), a.float(), dcoef)
+        d_ls = dscale.reshape(()).to(scale_dtype) if has_scale else None
+        return da.to(BF16), db.to(BF16), d_ls, None, None
+
+
 class _MilNceClipsFn(Function):
     """MIL-NCE with n clips per video (get_mil_nce_loss as driven by forward_stage1, univl_video_ret.py:146-197, :357-387):
         loss = mean_j( log( n * sum_i e^{<v_{j,c}, t_i>} + sum_{k != j, c'} e^{<t_j, v_{k,c'}>} ) - <v_{j,c}, t_j> - ln n ),   c = n // 2.
@@ -185,17 +275,39 @@ class _MilNceClipsFn(Function):
         return d_video.view(B * n, E).to(BF16), d_text.to(BF16), None, None
 
 
+_BACKENDS = ("gathered_grad", "two_sided")
+_backend = os.environ.get("B200MM_CONTRASTIVE", "gathered_grad")
+
+
+def set_backend(name):
+    """"gathered_grad" (default, hardware-verified): softmax-gradient tiles per block, gradients of the gathered rows reduce-scattered home.
+    "two_sided": grouped launches, two-sided gradient tiles, no gradient exchange (see _ContrastiveTwoSidedFn)."""
+    global _backend
+    if name not in _BACKENDS:
+        raise ValueError(f"contrastive backend {name!r}: expected one of {_BACKENDS}")
+    _backend = name
+
+
+def get_backend():
+    if _backend not in _BACKENDS:
+        raise ValueError(f"B200MM_CONTRASTIVE={_backend!r}: expected one of {_BACKENDS}")
+    return _backend
+
+
+def _fn():
+    return _ContrastiveTwoSidedFn if get_backend() == "two_sided" else _ContrastiveFn
+
+
 def clip_contrastive_loss(image_features, text_features, logit_scale, group=None):
     """Symmetric InfoNCE over the global batch; features [B, E] bf16 (normalised), logit_scale = log-temperature parameter."""
-    d = _ContrastiveFn.apply(image_features, text_features, logit_scale, "clip", group)
-    return d
+    return _fn().apply(image_features, text_features, logit_scale, "clip", group)
 
 
 def mil_nce_loss(video_features, text_features, group=None, n_clips=1):
     """UnivlForVideoTextRetrieval.get_mil_nce_loss (no temperature). video_features [B * n_clips, E] (clips of one video adjacent,
     as forward_img_encoder returns `clip_feature`), text_features [B, E]."""
     if n_clips == 1:
-        return _ContrastiveFn.apply(video_features, text_features, None, "mil", group)
+        return _fn().apply(video_features, text_features, None, "mil", group)
     if video_features.shape[0] != text_features.shape[0] * n_clips:
         raise ValueError("mil_nce_loss: video_features must hold n_clips rows per text row")
     return _MilNceClipsFn.apply(video_features.contiguous(), text_features.contiguous(), int(n_clips), group)

@@ -82,6 +82,17 @@ struct ContrastParams {
   int64_t n_valid;        // EPI_SOFTGRAD: columns >= n_valid are padding (G = 0 there)
   int32_t* rank_out;      // EPI_RANK: [M] += #{n : z[m,n] > row_lse[m], n != positive column}  (row_lse doubles as the reference logit)
   const int32_t* gt_col;  // EPI_RANK: [M] positive column of each row, or null -> m + diag_off
+  // EPI_SOFTGRAD, two-sided form: with col_lse the same logit tile also carries the gradient of the TRANSPOSED block (the other
+  // direction of a symmetric loss, whose rows are this block's columns):
+  //   dL/dz = coef * ( wr * exp(z - row_lse[m]) + wc * exp(z - col_lse[n]) - diag_sub * [diag] ),  wr / wc = 0 on the diagonal if *_diag_zero
+  const float* col_lse;   // [N] or null (one-sided form above)
+  int32_t row_diag_zero, col_diag_zero;
+  int32_t diag_exact;     // 1: the stored G leaves the -diag_sub term out (dscale still counts it): the caller adds -diag_sub*coef*alpha*b_{m+off}
+                          // to the row gradient in fp32, so the one large entry of a row is not rounded to bf16
+  // device-resident scalars (no host sync to read a parameter or the upstream gradient): alpha = *alpha_dev, coef *= *coef_dev
+  const float* alpha_dev;
+  const float* coef_dev;
+  void* D;                // EPI_SOFTGRAD output of THIS problem (grouped launches carry two problems, see GemmParams::n_prob)
 };
 
 enum { EPI_STD = 0, EPI_LSE = 1, EPI_SOFTGRAD = 2, EPI_RANK = 3 };
@@ -104,6 +115,10 @@ struct GemmParams {
   uint32_t wait_ns;  // > 0: epilogue warps wait for the accumulator with a suspending try_wait (hint in ns) instead of spinning
   EpiParams epi;
   ContrastParams con;
+  // grouped launch of the contrastive epilogues: problem 1 (same M, N, K, pitches of D) has its own operands (tmA2 / tmB2) and ContrastParams;
+  // its tiles follow problem 0's in the persistent schedule, so one launch fills the SMs where two half-empty waves ran before
+  int32_t n_prob;
+  ContrastParams con2;
 };
 
 // Full epilogue on 8 consecutive columns of one row (n % 8 == 0). Shared by the GEMM epilogue warps and the split-K
@@ -272,6 +287,7 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p) {
   TileCoord c;
   int64_t per_split = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  if (t >= per_split * p.splits) t -= per_split * p.splits;  // second problem of a grouped launch: same tile grid
   c.split = static_cast<int32_t>(t / per_split);
   int64_t rem = t - c.split * per_split;
   c.m_blk = static_cast<int32_t>(rem / p.n_tiles);
@@ -285,7 +301,8 @@ __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p)
 // FL == -1 keeps them as runtime values (any combination, edge flavours).
 template <bool A_MN, bool B_MN, int EPI, int CG, int FL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using PC = PairCfg<CG>;
   constexpr int STAGES = PC::NSTAGES;           // shadows the 1-CTA constants inside this kernel
   constexpr int STAGE_BYTES = PC::STAGE;
@@ -328,7 +345,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int64_t tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;  // a pair walks the macro-tile list together
 
-  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int64_t tiles_per_prob = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int64_t total_tiles = tiles_per_prob * (EPI == EPI_STD ? 1 : p.n_prob);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -336,6 +354,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
+      const bool second = EPI != EPI_STD && t >= tiles_per_prob;
+      const CUtensorMap* const pA = second ? &tmA2 : &tmA;
+      const CUtensorMap* const pB = second ? &tmB2 : &tmB;
       const int32_t m0 = tc.m_blk * (BM * CG) + static_cast<int32_t>(cta_rank) * BM;
       const int32_t n0 = tc.n_blk * BN + static_cast<int32_t>(cta_rank) * PC::BN_CTA;  // this CTA's share of the B tile
       for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
@@ -347,16 +368,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
             if constexpr (!A_MN) {
-              tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
+              tma_load_2d(pA, &full_bar[stage], sa, k0, m0);
             } else {
 #pragma unroll
-              for (int s = 0; s < BM / 64; ++s) tma_load_2d(&tmA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
+              for (int s = 0; s < BM / 64; ++s) tma_load_2d(pA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
             }
             if constexpr (!B_MN) {
-              tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+              tma_load_2d(pB, &full_bar[stage], sb, k0, n0);
             } else {
 #pragma unroll
-              for (int s = 0; s < BN / 64; ++s) tma_load_2d(&tmB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
+              for (int s = 0; s < BN / 64; ++s) tma_load_2d(pB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
             }
           } else {
             // both CTAs land their bytes on the LEADER's full barrier; only the leader arms it (for the pair's total)
@@ -433,6 +454,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
+      const ContrastParams& con = (EPI != EPI_STD && t >= tiles_per_prob) ? p.con2 : p.con;
+      const float alpha = (EPI != EPI_STD && con.alpha_dev != nullptr) ? *con.alpha_dev : p.epi.alpha;
       const int64_t m_cta = static_cast<int64_t>(tc.m_blk) * (BM * CG) + cta_rank * BM;  // first row of this CTA's 128
       const int64_t m = m_cta + quarter * 32 + lane;
       const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN;
@@ -543,7 +566,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else if constexpr (EPI == EPI_LSE) {
         // online (max, sum-exp) over this tile's columns of row m; the diagonal logit is captured on the way
         float mx = -INFINITY, sm = 0.f;
-        const int64_t dcol = m + p.con.diag_off;
+        const int64_t dcol = m + con.diag_off;
 #pragma unroll 1
         for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
@@ -554,7 +577,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float cm = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float z = nb + j < p.N ? __uint_as_float(r[j]) * p.epi.alpha : -INFINITY;
+              const float z = nb + j < p.N ? __uint_as_float(r[j]) * alpha : -INFINITY;
               r[j] = __float_as_uint(z);
               cm = fmaxf(cm, z);
             }
@@ -567,18 +590,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (m < p.M && dcol >= nb && dcol < nb + 32 && dcol < p.N) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (nb + j == dcol) p.con.diag[m] = __uint_as_float(r[j]);
+                if (nb + j == dcol) con.diag[m] = __uint_as_float(r[j]);
             }
           }
         }
         if (m < p.M) {
-          p.con.part_max[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = mx;
-          p.con.part_sum[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = sm;
+          con.part_max[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = mx;
+          con.part_sum[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = sm;
         }
       } else if constexpr (EPI == EPI_RANK) {
         // retrieval rank of the positive: how many logits of row m beat the reference logit (strictly), the positive itself excluded
-        const float ref = m < p.M ? p.con.row_lse[m] : INFINITY;
-        const int64_t dcol = m < p.M ? (p.con.gt_col != nullptr ? static_cast<int64_t>(p.con.gt_col[m]) : m + p.con.diag_off) : -1;
+        const float ref = m < p.M ? con.row_lse[m] : INFINITY;
+        const int64_t dcol = m < p.M ? (con.gt_col != nullptr ? static_cast<int64_t>(con.gt_col[m]) : m + con.diag_off) : -1;
         int cnt = 0;
 #pragma unroll 1
         for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
@@ -589,15 +612,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (nb < p.N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              cnt += (nb + j < p.N && nb + j != dcol && __uint_as_float(r[j]) * p.epi.alpha > ref) ? 1 : 0;
+              cnt += (nb + j < p.N && nb + j != dcol && __uint_as_float(r[j]) * alpha > ref) ? 1 : 0;
           }
         }
-        if (m < p.M && cnt) atomicAdd(p.con.rank_out + m, cnt);
+        if (m < p.M && cnt) atomicAdd(con.rank_out + m, cnt);
       } else {
-        const float lse = m < p.M ? p.con.row_lse[m] : 0.f;
-        const int64_t dcol = m + p.con.diag_off;
+        const float lse = m < p.M ? con.row_lse[m] : 0.f;
+        const int64_t dcol = m + con.diag_off;
+        const float coef = con.coef_dev != nullptr ? con.coef * *con.coef_dev : con.coef;
+        const bool two_sided = con.col_lse != nullptr;
         float ds_acc = 0.f;
-        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.epi.D) + m * p.epi.ldd;
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(con.D) + m * p.epi.ldd;
 #pragma unroll 1
         for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
@@ -611,12 +636,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float z = __uint_as_float(r[g * 8 + j]) * p.epi.alpha;
+                  const float z = __uint_as_float(r[g * 8 + j]) * alpha;
                   const bool on_diag = (n + j == dcol);
-                  float gz = p.con.coef * (__expf(z - lse) - (on_diag ? p.con.diag_sub : 0.f));
-                  if ((on_diag && p.con.diag_zero) || n + j >= p.con.n_valid) gz = 0.f;
+                  float gz;
+                  if (two_sided) {
+                    // this logit is also entry (n, m) of the transposed block, normalised there by col_lse[n]: both softmax terms at once
+                    const bool valid = n + j < con.n_valid;
+                    const float er = (on_diag && con.row_diag_zero) ? 0.f : __expf(z - lse);
+                    const float ec = (!valid || (on_diag && con.col_diag_zero)) ? 0.f : __expf(z - __ldg(con.col_lse + (valid ? n + j : 0)));
+                    gz = coef * (er + ec - (on_diag ? con.diag_sub : 0.f));
+                  } else {
+                    gz = coef * (__expf(z - lse) - (on_diag ? con.diag_sub : 0.f));
+                  }
+                  if ((on_diag && con.diag_zero) || n + j >= con.n_valid) gz = 0.f;
                   ds_acc += gz * z;
-                  v[j] = gz * p.epi.alpha;  // dL/d<a_m, b_n>
+                  if (two_sided && con.diag_exact && on_diag) gz += coef * con.diag_sub;
+                  v[j] = gz * alpha;  // dL/d<a_m, b_n>
                 }
                 uint4 o;
                 o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -626,9 +661,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (p.con.dscale != nullptr) {
+        if (con.dscale != nullptr) {
           ds_acc = warp_sum(ds_acc);
-          if (lane == 0) atomicAdd(p.con.dscale, ds_acc);
+          if (lane == 0) atomicAdd(con.dscale, ds_acc);
         }
       }
       tc_fence_before();
@@ -670,7 +705,8 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
 }
 
 template <bool A_MN, bool B_MN, int EPI, int CG, int FL = -1>
-static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream, const CUtensorMap* tmA2 = nullptr,
+                          const CUtensorMap* tmB2 = nullptr) {
   auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI, CG, FL>;
   constexpr int smem = PairCfg<CG>::SMEM;
   static bool attr_set = false;  // benign race: idempotent attribute
@@ -682,7 +718,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     }
     attr_set = true;
   }
-  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits * (EPI == EPI_STD || p.n_prob < 1 ? 1 : p.n_prob);
   const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs
   const int grid = static_cast<int>(total_tiles < units ? total_tiles : units) * CG;
   cudaLaunchConfig_t cfg = {};
@@ -697,7 +733,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2 ? *tmA2 : tmA, tmB2 ? *tmB2 : tmB, p);
   if (e != cudaSuccess) {
     set_last_error("gemm_tcgen05_kernel<CG=%d> launch: %s", CG, cudaGetErrorString(e));
     return B200MM_ERR_LAUNCH;
@@ -706,8 +742,9 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 template <bool A_MN, bool B_MN, int EPI = EPI_STD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  return launch_gemm_cg<A_MN, B_MN, EPI, 1>(tmA, tmB, p, stream);
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream, const CUtensorMap* tmA2 = nullptr,
+                       const CUtensorMap* tmB2 = nullptr) {
+  return launch_gemm_cg<A_MN, B_MN, EPI, 1>(tmA, tmB, p, stream, tmA2, tmB2);
 }
 
 // Merge per-tile (max, sum-exp) partials of up to two logit blocks into one log-sum-exp per row.
@@ -795,7 +832,8 @@ extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
   // the single-CTA kernels
   static const int cg_env = getenv("B200MM_GEMM_CG") ? atoi(getenv("B200MM_GEMM_CG")) : 2;
   const int cg = (cg_env == 2 && a->M > BM) ? 2 : 1;
-  GemmParams p;
+  GemmParams p = GemmParams{};
+  p.n_prob = 1;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_tiles = static_cast<int32_t>(ceil_div(a->M, BM * cg));
   p.n_tiles = static_cast<int32_t>(ceil_div(a->N, BN));
@@ -898,6 +936,7 @@ static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const 
                  "contrast: M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   B200MM_REQUIRE(a && b, B200MM_ERR_SHAPE, "contrast: null operand");
   p = GemmParams{};
+  p.n_prob = 1;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = static_cast<int32_t>(ceil_div(M, BM));
   p.n_tiles = static_cast<int32_t>(ceil_div(N, BN));
@@ -948,11 +987,61 @@ extern "C" int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* 
   if (rc) return rc;
   B200MM_REQUIRE(row_lse && G && N % 8 == 0 && ldg % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, B200MM_ERR_ALIGN,
                  "contrast_softgrad: G must be 16B aligned, N and ldg multiples of 8");
-  p.epi.D = G; p.epi.ldd = ldg;
+  p.epi.D = G; p.epi.ldd = ldg; p.con.D = G;
   p.con.row_lse = row_lse; p.con.coef = coef; p.con.diag_sub = diag_sub; p.con.diag_zero = diag_zero;
   p.con.diag_off = diag_off; p.con.dscale = dscale; p.con.n_valid = n_valid;
   if (b_mn) return launch_gemm<false, true, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<false, false, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- grouped (two problems per launch) forms for symmetric losses: problem 0 = rows a0 x columns b0, problem 1 = rows a1 x columns b1
+static int setup_pair(GemmParams& p, CUtensorMap (&tm)[4], const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1,
+                      const void* b1, int64_t ldb1, int64_t M, int64_t N, int64_t K, float alpha) {
+  int rc = setup_plain(p, tm[0], tm[1], a0, lda0, b0, ldb0, 0, M, N, K, alpha);
+  if (rc) return rc;
+  GemmParams q;
+  rc = setup_plain(q, tm[2], tm[3], a1, lda1, b1, ldb1, 0, M, N, K, alpha);
+  if (rc) return rc;
+  p.n_prob = 2;
+  return B200MM_OK;
+}
+
+extern "C" int b200mm_contrast_lse_partials_pair(const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1,
+                                                 const void* b1, int64_t ldb1, int64_t M, int64_t N, int64_t K, float alpha,
+                                                 const float* alpha_dev, int64_t diag_off, float* part_max0, float* part_sum0, float* diag0,
+                                                 float* part_max1, float* part_sum1, float* diag1, void* stream) {
+  GemmParams p;
+  CUtensorMap tm[4];
+  int rc = setup_pair(p, tm, a0, lda0, b0, ldb0, a1, lda1, b1, ldb1, M, N, K, alpha);
+  if (rc) return rc;
+  B200MM_REQUIRE(part_max0 && part_sum0 && diag0 && part_max1 && part_sum1 && diag1, B200MM_ERR_SHAPE, "contrast_lse_partials_pair: null output");
+  p.con.part_max = part_max0; p.con.part_sum = part_sum0; p.con.diag = diag0; p.con.diag_off = diag_off; p.con.alpha_dev = alpha_dev;
+  p.con2 = p.con;
+  p.con2.part_max = part_max1; p.con2.part_sum = part_sum1; p.con2.diag = diag1;
+  return launch_gemm<false, false, EPI_LSE>(tm[0], tm[1], p, reinterpret_cast<cudaStream_t>(stream), &tm[2], &tm[3]);
+}
+
+extern "C" int b200mm_contrast_softgrad_pair(const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1, const void* b1,
+                                             int64_t ldb1, int64_t M, int64_t N, int64_t K, int64_t n_valid, float alpha, const float* alpha_dev,
+                                             int64_t diag_off, const float* row_lse0, const float* col_lse0, const float* row_lse1,
+                                             const float* col_lse1, float coef, const float* coef_dev, float diag_sub, int32_t row_diag_zero0,
+                                             int32_t col_diag_zero0, int32_t row_diag_zero1, int32_t col_diag_zero1, void* G0, void* G1, int64_t ldg,
+                                             float* dscale, void* stream) {
+  GemmParams p;
+  CUtensorMap tm[4];
+  int rc = setup_pair(p, tm, a0, lda0, b0, ldb0, a1, lda1, b1, ldb1, M, N, K, alpha);
+  if (rc) return rc;
+  B200MM_REQUIRE(row_lse0 && col_lse0 && row_lse1 && col_lse1 && G0 && G1 && N % 8 == 0 && ldg % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(G0) & 15) == 0 && (reinterpret_cast<uintptr_t>(G1) & 15) == 0,
+                 B200MM_ERR_ALIGN, "contrast_softgrad_pair: row / column LSEs required; G 16B aligned, N and ldg multiples of 8");
+  p.epi.D = G0; p.epi.ldd = ldg;
+  p.con.D = G0; p.con.row_lse = row_lse0; p.con.col_lse = col_lse0; p.con.coef = coef; p.con.coef_dev = coef_dev; p.con.diag_sub = diag_sub;
+  p.con.row_diag_zero = row_diag_zero0; p.con.col_diag_zero = col_diag_zero0; p.con.diag_off = diag_off; p.con.dscale = dscale;
+  p.con.n_valid = n_valid; p.con.alpha_dev = alpha_dev; p.con.diag_exact = 1;
+  p.con2 = p.con;
+  p.con2.D = G1; p.con2.row_lse = row_lse1; p.con2.col_lse = col_lse1; p.con2.row_diag_zero = row_diag_zero1; p.con2.col_diag_zero = col_diag_zero1;
+  p.con2.dscale = nullptr;  // every logit pair is visited by both problems: the log-temperature gradient is taken from problem 0 only
+  return launch_gemm<false, false, EPI_SOFTGRAD>(tm[0], tm[1], p, reinterpret_cast<cudaStream_t>(stream), &tm[2], &tm[3]);
 }
 
 extern "C" int b200mm_contrast_rank(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,

@@ -453,6 +453,55 @@ def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, d
     return G
 
 
+def contrast_lse_partials_pair(a0, b0, a1, b1, alpha, diag_off, alpha_dev=None):
+    """Both directions of a symmetric loss in one grouped launch: ((pmax0, psum0, diag0), (pmax1, psum1, diag1)) for z0 = alpha a0·b0^T and
+    z1 = alpha a1·b1^T (same shapes). alpha_dev: device f32 scalar that replaces `alpha` (no host read of the temperature)."""
+    lib = _lib.load()
+    M, K = a0.shape
+    N = b0.shape[0]
+    if tuple(a1.shape) != (M, K) or tuple(b1.shape) != (N, K):
+        raise _lib.B200mmError("b200mm.contrast_lse_partials_pair: the two problems must have the same shapes")
+    nt = lib.b200mm_contrast_num_tiles(N)
+    outs = []
+    for _ in range(2):
+        pmax = torch.empty((M, nt), device=a0.device, dtype=torch.float32)
+        outs.append((pmax, torch.empty_like(pmax), torch.zeros(M, device=a0.device, dtype=torch.float32)))
+    if alpha_dev is not None:
+        _req(alpha_dev, "alpha_dev", torch.float32)
+    _lib.check(lib.b200mm_contrast_lse_partials_pair(_ptr(a0), _row_major_2d(a0, "a0"), _ptr(b0), _row_major_2d(b0, "b0"), _ptr(a1),
+                                                     _row_major_2d(a1, "a1"), _ptr(b1), _row_major_2d(b1, "b1"), M, N, K, float(alpha),
+                                                     _ptr(alpha_dev), diag_off, _ptr(outs[0][0]), _ptr(outs[0][1]), _ptr(outs[0][2]),
+                                                     _ptr(outs[1][0]), _ptr(outs[1][1]), _ptr(outs[1][2]), _stream()),
+               "b200mm_contrast_lse_partials_pair")
+    _count(1)
+    return outs[0], outs[1]
+
+
+def contrast_softgrad_pair(a0, b0, a1, b1, n_valid, alpha, diag_off, row_lse0, col_lse0, row_lse1, col_lse1, coef, diag_sub, zero_flags, dscale,
+                           alpha_dev=None, coef_dev=None):
+    """Two-sided softmax-gradient tiles of both directions in one grouped launch (include/b200mm.h: b200mm_contrast_softgrad_pair):
+    G_k[m, n] = alpha*coef*(wr exp(z_k - row_lse_k[m]) + wc exp(z_k - col_lse_k[n]) - diag_sub [diag]) as bf16 [M, N];
+    zero_flags = (row_diag_zero0, col_diag_zero0, row_diag_zero1, col_diag_zero1); dscale (f32 [1] or None) += sum dL/dz z over problem 0."""
+    lib = _lib.load()
+    M, K = a0.shape
+    N = b0.shape[0]
+    if tuple(a1.shape) != (M, K) or tuple(b1.shape) != (N, K):
+        raise _lib.B200mmError("b200mm.contrast_softgrad_pair: the two problems must have the same shapes")
+    for t, nm, n_ in ((row_lse0, "row_lse0", M), (row_lse1, "row_lse1", M), (col_lse0, "col_lse0", n_valid), (col_lse1, "col_lse1", n_valid)):
+        _req(t, nm, torch.float32, 1)
+        if t.numel() < n_ or not t.is_contiguous():
+            raise _lib.B200mmError(f"b200mm.contrast_softgrad_pair: {nm} must be contiguous with >= {n_} entries")
+    G0 = torch.empty((M, N), device=a0.device, dtype=BF16)
+    G1 = torch.empty((M, N), device=a0.device, dtype=BF16)
+    _lib.check(lib.b200mm_contrast_softgrad_pair(_ptr(a0), _row_major_2d(a0, "a0"), _ptr(b0), _row_major_2d(b0, "b0"), _ptr(a1),
+                                                 _row_major_2d(a1, "a1"), _ptr(b1), _row_major_2d(b1, "b1"), M, N, K, n_valid, float(alpha),
+                                                 _ptr(alpha_dev), diag_off, _ptr(row_lse0), _ptr(col_lse0), _ptr(row_lse1), _ptr(col_lse1),
+                                                 float(coef), _ptr(coef_dev), float(diag_sub), *[int(z) for z in zero_flags], _ptr(G0), _ptr(G1), N,
+                                                 _ptr(dscale), _stream()), "b200mm_contrast_softgrad_pair")
+    _count(1)
+    return G0, G1
+
+
 def contrast_rank(a, b, alpha, ref, diag_off=0, gt_col=None, b_mn=False):
     """rank[m] = #{n != pos(m): alpha*<a_m, b_n> > ref[m]} (int32 [M]); pos(m) = gt_col[m] (int32) or m + diag_off.
     The [M, N] similarity only exists tile by tile in TMEM."""

@@ -160,6 +160,28 @@ int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t 
                              int64_t n_valid,
                              float alpha, int64_t diag_off, const float* row_lse, float coef, float diag_sub, int32_t diag_zero,
                              void* G, int64_t ldg, float* dscale, void* stream);
+/* Symmetric losses, both directions per launch (grouped: problem 0 = rows a0 x columns b0, problem 1 = rows a1 x columns b1, same M, N, K;
+ * one persistent launch fills the SMs where two half-empty tile waves ran before). alpha_dev / coef_dev (device f32 scalars, may be null)
+ * replace alpha / multiply coef, so neither exp(logit_scale) nor the upstream gradient has to be read back by the host.
+ *   lse_partials_pair: the lse_partials outputs of both problems.
+ *   softgrad_pair    : TWO-SIDED gradient tiles. Logit z[m,n] of problem 0 is also entry (n, m) of problem 1's block on the rank that owns
+ *                      row n, where it is normalised by that row's LSE; with the row LSEs of ALL ranks gathered (col_lse [N]) a rank forms
+ *                        G[m,n] = alpha*coef*( wr*exp(z - row_lse[m]) + wc*exp(z - col_lse[n]) - diag_sub*[n == m+diag_off] )
+ *                      (wr / wc = 0 on the diagonal if row_diag_zero / col_diag_zero: MIL-NCE's excluded own-video logit), and
+ *                      d a_m = sum_n G[m,n] b_n is the COMPLETE gradient of the global loss w.r.t. its own rows: no gradient exchange
+ *                      (the reduce-scatter of GradientAllGather.backward, antmmf/utils/distributed_utils.py:104-116, is replaced by an
+ *                      all-gather of 2*B floats in forward). dscale (problem 0 only) += sum dL/dz * z.
+ *                      The stored G leaves the diagonal's -diag_sub term OUT (dscale counts it): the caller adds
+ *                      -diag_sub*coef*alpha*b_{m+diag_off} to row m's gradient in fp32, so the one large entry of a row is never rounded to bf16. */
+int b200mm_contrast_lse_partials_pair(const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1, const void* b1,
+                                      int64_t ldb1, int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev, int64_t diag_off,
+                                      float* part_max0, float* part_sum0, float* diag0, float* part_max1, float* part_sum1, float* diag1,
+                                      void* stream);
+int b200mm_contrast_softgrad_pair(const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1, const void* b1,
+                                  int64_t ldb1, int64_t M, int64_t N, int64_t K, int64_t n_valid, float alpha, const float* alpha_dev,
+                                  int64_t diag_off, const float* row_lse0, const float* col_lse0, const float* row_lse1, const float* col_lse1,
+                                  float coef, const float* coef_dev, float diag_sub, int32_t row_diag_zero0, int32_t col_diag_zero0,
+                                  int32_t row_diag_zero1, int32_t col_diag_zero1, void* G0, void* G1, int64_t ldg, float* dscale, void* stream);
 /* Retrieval rank of the positive pair without materialising the similarity matrix — replaces the sort-based rank of
  * _compute_retrieval_metrics (antmmf/modules/metrics/global_retrieval_recall.py:12-27) and cal_ret_metric
  * (prj/base_vtp/roi_univl/univl/model/univl_video_pretrain.py:294-312):

@@ -310,6 +310,40 @@ def contrast_softgrad(a, b, n_valid, alpha, diag_off, row_lse, coef, diag_sub, d
     return (alpha * dz).to(BF)
 
 
+def contrast_lse_partials_pair(a0, b0, a1, b1, alpha, diag_off, alpha_dev=None):
+    al = float(alpha_dev) if alpha_dev is not None else alpha
+    return contrast_lse_partials(a0, b0, al, diag_off), contrast_lse_partials(a1, b1, al, diag_off)
+
+
+def contrast_softgrad_pair(a0, b0, a1, b1, n_valid, alpha, diag_off, row_lse0, col_lse0, row_lse1, col_lse1, coef, diag_sub, zero_flags, dscale,
+                           alpha_dev=None, coef_dev=None):
+    al = float(alpha_dev) if alpha_dev is not None else alpha
+    cf = coef * (float(coef_dev) if coef_dev is not None else 1.0)
+    outs = []
+    for k, (a, b, rl, cl) in enumerate(((a0, b0, row_lse0, col_lse0), (a1, b1, row_lse1, col_lse1))):
+        z = _logits(a, b, al, False)
+        M, N = z.shape
+        er = torch.exp(z - rl[:, None])
+        clp = torch.zeros(N)
+        clp[:n_valid] = cl[:n_valid]
+        ec = torch.exp(z - clp[None, :])
+        cols = torch.arange(M) + diag_off
+        ok = (cols >= 0) & (cols < N)
+        r = torch.arange(M)[ok]
+        if zero_flags[2 * k]:
+            er[r, cols[ok]] = 0.0
+        if zero_flags[2 * k + 1]:
+            ec[r, cols[ok]] = 0.0
+        dz = cf * (er + ec)
+        dz[:, n_valid:] = 0.0
+        full = dz.clone()
+        full[r, cols[ok]] -= cf * diag_sub
+        if k == 0 and dscale is not None:
+            dscale += (full * z).sum()
+        outs.append((al * dz).to(BF))  # the stored tiles leave the -diag_sub term to the caller (exact, fp32)
+    return outs[0], outs[1]
+
+
 def contrast_rank(a, b, alpha, ref, diag_off=0, gt_col=None, b_mn=False):
     z = _logits(a, b, alpha, b_mn)
     M, N = z.shape

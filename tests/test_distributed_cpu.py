@@ -234,7 +234,11 @@ WORKER_LOSSES = textwrap.dedent(
 )
 
 
-def test_world2_gloo_contrastive_losses_host_code(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("backend", ["gathered_grad", "two_sided"])
+def test_world2_gloo_contrastive_losses_host_code(tmp_path, backend):
     """The production host code of the sharded losses (b200mm.contrastive._ContrastiveFn / _MilNceClipsFn: padded all-gather, per-rank
     logit blocks, W x local share, reduce-scatter of remote-row gradients) on 2 gloo ranks over the torch stand-ins of the kernels — vs
     the full-batch oracle: mean over ranks of the loss = global loss, DDP-averaged gradients = global gradient."""
@@ -242,6 +246,7 @@ def test_world2_gloo_contrastive_losses_host_code(tmp_path):
     script.write_text(WORKER_LOSSES % ROOT)
     port = 29800 + (os.getpid() % 90)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, B200MM_CONTRASTIVE=backend))  # "two_sided": LSE all-gather instead of the gradient reduce-scatter
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert (tmp_path / "ok3_0").exists() and (tmp_path / "ok3_1").exists()

@@ -87,6 +87,33 @@ def run(B, Bg, E, alpha=14.285):
         da_all = ops.gemm(GB, b, a_mn=True, b_mn=True, out_f32=True)
         return da, db, da_all, db_all
 
+    # round 2: both directions per grouped launch, two-sided gradient tiles (no gathered-row gradient GEMMs, no reduce-scatter), device scalars
+    alpha_dev = torch.full((1,), alpha, device="cuda")
+    gout = torch.ones(1, device="cuda")
+
+    def fwd2():
+        pA, pB = ops.contrast_lse_partials_pair(a, b_all, b, a_all, 1.0, off, alpha_dev=alpha_dev)
+        loss = torch.zeros(1, device="cuda")
+        state["lseA"] = ops.contrast_lse_merge(pA[:2], None, pA[2], False, loss)
+        state["lseB"] = ops.contrast_lse_merge(pB[:2], None, pB[2], False, loss)
+        return loss
+
+    def bwd2():
+        ds = torch.zeros(1, device="cuda")
+        GA, GB = ops.contrast_softgrad_pair(a, b_all, b, a_all, Bg, 1.0, off, state["lseA"], state["lseB_all"], state["lseB"], state["lseA_all"],
+                                            1.0 / (2 * Bg), 2.0, (0, 0, 0, 0), ds, alpha_dev=alpha_dev, coef_dev=gout)
+        dcoef = gout * (-2.0 / (2 * Bg)) * alpha_dev
+        da = torch.addcmul(ops.gemm(GA, b_all, b_mn=True, out_f32=True), b.float(), dcoef)
+        db = torch.addcmul(ops.gemm(GB, a_all, b_mn=True, out_f32=True), a.float(), dcoef)
+        return da.to(BF), db.to(BF), ds
+
+    fwd()
+    # the row LSEs of the other ranks (what the forward all-gathers): here the LSE of every gathered row against this rank's columns is
+    # not the real thing, but the kernel's work is identical — use full-width LSEs computed once with torch
+    state["lseA_all"] = torch.logsumexp(alpha * a_all.float() @ b_all.float().t(), 1)
+    state["lseB_all"] = torch.logsumexp(alpha * b_all.float() @ a_all.float().t(), 1)
+    v1 = (timeit_graph(fwd), timeit_graph(bwd))
+    fwd, bwd = fwd2, bwd2
     fwd()
     t_f_eager, t_b_eager = timeit(fwd), timeit(bwd)
     try:  # the headline figures: device time without host launch cost (in training these launches queue behind the encoder kernels)
@@ -97,7 +124,7 @@ def run(B, Bg, E, alpha=14.285):
     fl_f, fl_b = 4.0 * B * Bg * E, 12.0 * B * Bg * E
     bytes_alg = 2 * Bg * E * 2 + 2 * Bg * E * 2 + 2 * Bg * 4  # read gathered I,T; write their gradients (bf16); LSE vectors
     # what this implementation additionally moves: the bf16 softmax-gradient blocks G [B, B_g] x 2, written once and read twice
-    bytes_g = 2 * B * Bg * 2 * 3
+    bytes_g = 2 * B * Bg * 2 * 2  # round 2: written once, read once
 
     # the reference's arithmetic, unfused, by torch on the same GPU: fp32 logits of this rank's rows, log_softmax, autograd
     af, bf_ = a.float().requires_grad_(), b.float().requires_grad_()
@@ -130,6 +157,7 @@ def run(B, Bg, E, alpha=14.285):
     t = t_f + t_b
     out = {
         "shape": {"B_local": B, "B_global": Bg, "E": E},
+        "round1_launch_sequence_ms": {"fwd": round(v1[0], 4), "bwd": round(v1[1], 4), "total": round(v1[0] + v1[1], 4)},
         "timing": timing, "fwd_ms": round(t_f, 4), "bwd_ms": round(t_b, 4), "total_ms": round(t, 4),
         "eager_launch_fwd_ms": round(t_f_eager, 4), "eager_launch_bwd_ms": round(t_b_eager, 4),
         "tflops": round((fl_f + fl_b) / t / 1e9, 1), "frac_of_sustained_bf16_peak": round((fl_f + fl_b) / t / 1e9 / PEAK_TF, 3),
