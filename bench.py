@@ -345,6 +345,11 @@ def run_ours(args):
     out = None
     if rank == 0:
         fpp = FLOP_PER_PAIR.get(args.model)
+        if args.model in ("ViT-H-14", "ViT-L-14") and (res != 224 or L != 77):
+            # the table entries are for 224^2 / 77 tokens: same counting rule at the resolution / text length actually run (configs[4]: 336^2)
+            vw, vl, tw, tl, ps = (1280, 32, 1024, 24, 14) if args.model == "ViT-H-14" else (1024, 24, 768, 12, 14)
+            li = (res // ps) ** 2 + 1
+            fpp = 3 * ((24 * vw**2 + 4 * li * vw) * vl * li + (24 * tw**2 + 4 * L * tw) * tl * L)
         if args.model.startswith("base_vtp"):
             # per pair, fwd+bwd = 3 x (8 frames of ViT-B/16 + BERT-base at L + B cross-encoder passes over L + 2 tokens): hard mining scores every
             # text against B videos, so the cross-encoder work per pair grows with the per-GPU batch
