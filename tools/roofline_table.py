@@ -2,7 +2,7 @@
 shapes, T = 263 168 token rows = 1024 images x 257 tokens, width 1024): measured time and DRAM bytes next to the kernel's ALGORITHMIC
 work (tools/prof_kernels.py shapes), achieved TFLOP/s or GB/s, and the fraction of the measured B200 peak that bounds it.
 
-  python tools/roofline_table.py > profiles/r01k_roofline_table.md
+  python tools/roofline_table.py > profiles/r02a_roofline_table.md
 """
 import json
 import os
@@ -23,8 +23,9 @@ work = {
     "attn_bwd_tc_kernel": ("attention bwd (dQ, dK, dV in one kernel)", "tensor/MUFU", 10.0 * NB * H * L * L * HD, bf * 8 * T * W),
     "attn_dsum_kernel": ("D = rowsum(dO * O)", "hbm", 0, bf * 2 * T * W),
     "ln_fwd_plain_kernel<4>": ("LayerNorm fwd [T,1024]", "hbm", 0, bf * 2 * T * W),
-    # (tools/prof_kernels.py passed dadd = dy in this capture: 2 distinct tensors read + 1 written)
-    "ln_bwd_plain_kernel<4, 1>": ("LayerNorm bwd + residual-gradient add [T,1024] (dadd aliased dy in this capture)", "hbm", 0, bf * 3 * T * W),
+    # (round 2: tools/prof_kernels.py passes a distinct tensor as the residual-branch gradient: dy, x, dadd read + dx written; the round-1
+    # capture aliased dadd = dy and under-counted the kernel's bytes, which is where its "0.74 of HBM" came from)
+    "ln_bwd_plain_kernel<4, 1>": ("LayerNorm bwd + residual-gradient add [T,1024] (dy, x, dadd read; dx written)", "hbm", 0, bf * 4 * T * W),
     "rowsum_periodic_kernel": ("bias gradient: column sums of [T,4096]", "hbm", 0, bf * T * 4096),
     "act_fwd_kernel": ("QuickGELU recompute [T,4096]", "hbm", 0, bf * 2 * T * 4096),
     "act_ln_fwd_kernel<4, 128, 2, 1>": ("M2 sub-LN fwd: LN(gelu(u)) [T,4096]", "hbm (issue/MUFU-limited)", 0, bf * 2 * T * 4096),
