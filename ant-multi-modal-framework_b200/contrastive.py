@@ -95,27 +95,32 @@ class _ContrastiveFn(Function):
             denom = float(Bg)
         else:
             raise ValueError(f"unknown contrastive mode {mode!r}")
-        ctx.save_for_backward(a, b, a_all, b_all, lseA, lseB)
+        ctx.save_for_backward(a, b, a_all, b_all, lseA, lseB, partsA[2], partsB[2])
         ctx.meta = (mode, group, alpha, off, Bg, denom, world, log_scale.dtype if log_scale is not None else None)
         # W * local share: mean over ranks == global loss (see module docstring)
         return (loss_sum * (world / denom)).reshape(())
 
     @staticmethod
     def backward(ctx, gout):
-        a, b, a_all, b_all, lseA, lseB = ctx.saved_tensors
+        a, b, a_all, b_all, lseA, lseB, diagA, diagB = ctx.saved_tensors
         mode, group, alpha, off, Bg, denom, world, scale_dtype = ctx.meta
         has_scale = scale_dtype is not None
         B, E = a.shape
         coef = float(gout) * world / denom
         dscale = torch.zeros(1, device=a.device, dtype=torch.float32) if has_scale else None
-        # dL/dA and dL/dBt as bf16 [B, Bg_pad]; both blocks are softmax-minus-onehot of their row LSE
+        # dL/dA and dL/dBt as bf16 [B, Bg_pad]: softmax of the row LSE. The "minus one-hot" of the positive is kept OUT of the bf16 tiles
+        # (diag_sub = 0) and applied below in fp32: it is the one large entry of a row (≈ -coef against probabilities of ≈ coef / B_g), and
+        # batch-summed parameter gradients are small residuals of these rows — rounding that entry to bf16 cost 19 % / 35 % on bias
+        # gradients at 2 / 8 ranks (profiles/r02d_…, r02e_mgpu_parity_8ranks.log; reproduced in tests/test_sharded_grad_storage_cpu.py)
         if mode == "clip":
-            GA = ops.contrast_softgrad(a, b_all, Bg, alpha, off, lseA, coef, 1.0, False, dscale)
-            GB = ops.contrast_softgrad(b, a_all, Bg, alpha, off, lseB, coef, 1.0, False, dscale)
+            GA = ops.contrast_softgrad(a, b_all, Bg, alpha, off, lseA, coef, 0.0, False, dscale)
+            GB = ops.contrast_softgrad(b, a_all, Bg, alpha, off, lseB, coef, 0.0, False, dscale)
+            n_pos = 2.0   # the positive pair (i, i) is the target of row i in both blocks
         else:
             # union row: the positive appears once (in A); Bt's diagonal is excluded
-            GA = ops.contrast_softgrad(a, b_all, Bg, alpha, off, lseA, coef, 1.0, False, dscale)
+            GA = ops.contrast_softgrad(a, b_all, Bg, alpha, off, lseA, coef, 0.0, False, dscale)
             GB = ops.contrast_softgrad(b, a_all, Bg, alpha, off, lseB, coef, 0.0, True, dscale)
+            n_pos = 1.0
         # local-row gradients:  da = GA · b_all,  db = GB · a_all        (B operand read MN-major: [K = Bg_pad, N = E])
         da = ops.gemm(GA, b_all, b_mn=True, out_f32=True)
         db = ops.gemm(GB, a_all, b_mn=True, out_f32=True)
@@ -125,9 +130,15 @@ class _ContrastiveFn(Function):
         ops.gemm(GB, b, a_mn=True, b_mn=True, out_f32=True, out=d_all[:, :E])
         ops.gemm(GA, a, a_mn=True, b_mn=True, out_f32=True, out=d_all[:, E:])
         home = _scatter_grad(d_all, B, group)
-        da = da + home[:, :E]
-        db = db + home[:, E:]
-        d_ls = dscale.reshape(()).to(scale_dtype) if has_scale else None
+        # the positives' terms, exact: dL/dz_ii carries -coef per block that targets it; z_ii = alpha <a_i, b_i> (b_i = row off + i of b_all, a
+        # local row: its gathered-row gradient comes home to this rank, so both sides are added here)
+        c = n_pos * coef * alpha
+        da = torch.add(da + home[:, :E], b.float(), alpha=-c)
+        db = torch.add(db + home[:, E:], a.float(), alpha=-c)
+        d_ls = None
+        if has_scale:
+            # d/d(log scale) = sum dL/dz * z: the tiles' share is in dscale, the positives' is -coef * (z_ii per targeting block)
+            d_ls = (dscale.reshape(()) - coef * (diagA.sum() + (diagB.sum() if mode == "clip" else 0.0))).to(scale_dtype)
         return da.to(BF16), db.to(BF16), d_ls, None, None
 
 

@@ -48,5 +48,14 @@ Other measured parity points of round 2 (logs under `profiles/`):
 | sharded losses vs the oracle on the gathered batch, 2 ranks: MIL-NCE (1 and 2 clips) loss 1e-7, feature gradients 2e-3; MoCo gather + queue NCE exact / 1.7e-3 | OK | `r02d_mgpu_parity_2ranks.log` |
 | the same at 8 ranks (global batch 80 / 96) | OK (2.5e-3 / 2.6e-3 / 1.8e-3) | `r02e_mgpu_parity_8ranks.log` |
 | sharded symmetric InfoNCE through the 2-layer model, loss vs oracle | 3.20072 vs 3.20030 (2 ranks), 4.59452 vs 4.59441 (8 ranks) | same logs |
-| ... its parameter gradients vs the fp32 oracle | **open**: worst rel-L2 0.12 (2 ranks, `visual.ln_post.bias`), 0.35 (8 ranks, a BERT value bias; 10 × the eager-bf16 calibrator) — bias gradients are batch sums of nearly cancelling per-sample terms; the single-process run of the same global batch was not measured before the GPU budget ran out, so sharding and kernel precision are not yet separated. The round-1 check (sharded vs single-process b200mm, 4e-2) passed on the same code path. | same logs |
+| ... its parameter gradients vs the fp32 oracle (mid-round build) | worst rel-L2 0.12 (2 ranks, `visual.ln_post.bias`), 0.35 (8 ranks, a BERT value bias; 10 × the eager-bf16 calibrator) | same logs |
+
+The last row was traced after the GPU budget had run out, on the CPU: `tests/test_sharded_grad_storage_cpu.py` replays what every rank does
+over the emulated kernels and, with the mid-round code, reproduced the hardware figures (same worst parameters, 0.19 and 0.355). Cause: the
+softmax-gradient tiles G were stored in bf16 INCLUDING the positive's "minus one-hot" entry; at random initialisation batch-summed parameter
+gradients are residuals ≈ 20 × smaller than one rank's partial sum (|partial| 0.16 vs |global| 0.0077 for `ln_post.bias`), and 2⁻⁹ of that one
+large entry per row does not cancel. Fix (both contrastive backends, host side only — the kernels are called with `diag_sub = 0` and the
+positives' term is added to the row gradients and to the log-temperature gradient in fp32): worst parameter **0.055 / 0.049** at 2 / 8 ranks in
+the same replay, level with the eager-bf16 reference arithmetic (0.05). The hardware re-run of `tests/mgpu_worker.py` with the fix is the
+first item of the next GPU session; the round-end single-GPU suite exercises the same backward through `tests/test_model_gpu.py`.
 """)
