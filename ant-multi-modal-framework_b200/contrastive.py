@@ -272,7 +272,8 @@ class _MilNceClipsFn(Function):
         coef = float(gout) * world / Bg
         ln_n = float(torch.log(torch.tensor(float(n))))
         # dL/dA = coef * (n e^{z - total} - [i == j]);  dL/dBt = coef * e^{z - total}, zero on the own video's clips
-        GA = ops.contrast_softgrad(v_mid, t_all, Bg, 1.0, off, (total - ln_n).contiguous(), coef, 1.0, False, None)
+        # (the positive's -coef entry is kept out of the bf16 tiles and added in fp32 below, as in _ContrastiveFn)
+        GA = ops.contrast_softgrad(v_mid, t_all, Bg, 1.0, off, (total - ln_n).contiguous(), coef, 0.0, False, None)
         GB = ops.contrast_softgrad(text, v_all, Bg * n, 1.0, ops.NO_DIAG, total, coef, 0.0, False, None)
         rows = torch.arange(B, device=text.device)
         GB[:, : Bg * n].view(B, Bg, n)[rows, rows + off] = 0
@@ -280,9 +281,9 @@ class _MilNceClipsFn(Function):
         d_text = ops.gemm(GB, v_all, b_mn=True, out_f32=True)                       # [B, E]
         d_t_all = ops.gemm(GA, v_mid, a_mn=True, b_mn=True, out_f32=True)           # [Bg_pad, E]
         d_v_all = ops.gemm(GB, text, a_mn=True, b_mn=True, out_f32=True)            # [(Bg*n)_pad, E]
-        d_text = d_text + _scatter_grad(d_t_all, B, group)
+        d_text = torch.add(d_text + _scatter_grad(d_t_all, B, group), v_mid.float(), alpha=-coef)    # positive <v_mid_j, t_j>: row j of block A
         d_video = _scatter_grad(d_v_all, B * n, group).clone().view(B, n, E)
-        d_video[:, n // 2] += d_vmid
+        d_video[:, n // 2] += torch.add(d_vmid, text.float(), alpha=-coef)
         return d_video.view(B * n, E).to(BF16), d_text.to(BF16), None, None
 
 
