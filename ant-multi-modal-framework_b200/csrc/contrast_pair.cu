@@ -1,19 +1,12 @@
-// b200mm — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+// b200mm — grouped contrastive-loss kernels for the opt-in "two_sided" backend (b200mm_contrast_lse_partials_pair /
+// b200mm_contrast_softgrad_pair, include/b200mm.h): both directions of a symmetric loss per launch, two-sided softmax-gradient tiles,
+// device-resident scalars.
 //
-//   D[M,N] = epilogue(alpha * A[M,K] · B[N,K]^T)      bf16 operands, fp32 accumulation in TMEM
-//
-// Replaces nn.Linear / matmul on the ViT+BERT path (see include/b200mm.h for the reference call sites) in
-// forward (A=x, B=W), dgrad (A=dY, B=W read MN-major) and wgrad (A=dY, B=x, both MN-major) form, so no operand
-// is ever transposed through HBM.
-//
-// Structure (one CTA per SM, 256 threads, static round-robin tile schedule):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D boxes into a 4-stage 128B-swizzled smem ring
-//   warp 1      MMA issuer: one lane issues tcgen05.mma 128x256x16 (SS operands), accumulators in TMEM,
-//               tcgen05.commit releases smem stages and publishes finished accumulators
-//   warp 2      TMEM allocator (512 columns = 2 accumulator stages of 256 fp32 columns)
-//   warps 4..11 epilogue (lane quarter = warp % 4, column half = (warp-4) / 4): tcgen05.ld 32 columns at a time ->
-//               warp-private smem transpose -> bias/activation/residual with row-segment-coalesced 16B global accesses;
-//               runs concurrently with the next tile's mainloop thanks to the double-buffered accumulator
+// The kernel is the warp-specialised single-CTA tcgen05 GEMM of gemm_tcgen05.cu (TMA producer warp, single-lane MMA issuer, TMEM
+// double-buffered accumulators, epilogue warps) instantiated for the two contrastive epilogues, plus: a second problem (own tensor maps and
+// ContrastParams) whose tiles follow the first one's in the persistent schedule, the column-LSE term of the two-sided gradient, alpha / coef
+// read from device memory. It lives in its OWN translation unit on purpose: it was written after round 2's GPU budget was spent and has not
+// run on hardware yet, and gemm_tcgen05.cu — every verified GEMM of the path — stays byte-identical to the build the GPU tests passed on.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -21,6 +14,7 @@
 #include <type_traits>
 
 namespace b200mm {
+namespace pair {
 
 constexpr int BM = 128;
 constexpr int BN = 256;
@@ -82,6 +76,17 @@ struct ContrastParams {
   int64_t n_valid;        // EPI_SOFTGRAD: columns >= n_valid are padding (G = 0 there)
   int32_t* rank_out;      // EPI_RANK: [M] += #{n : z[m,n] > row_lse[m], n != positive column}  (row_lse doubles as the reference logit)
   const int32_t* gt_col;  // EPI_RANK: [M] positive column of each row, or null -> m + diag_off
+  // EPI_SOFTGRAD, two-sided form: with col_lse the same logit tile also carries the gradient of the TRANSPOSED block (the other
+  // direction of a symmetric loss, whose rows are this block's columns):
+  //   dL/dz = coef * ( wr * exp(z - row_lse[m]) + wc * exp(z - col_lse[n]) - diag_sub * [diag] ),  wr / wc = 0 on the diagonal if *_diag_zero
+  const float* col_lse;   // [N] or null (one-sided form above)
+  int32_t row_diag_zero, col_diag_zero;
+  int32_t diag_exact;     // 1: the stored G leaves the -diag_sub term out (dscale still counts it): the caller adds -diag_sub*coef*alpha*b_{m+off}
+                          // to the row gradient in fp32, so the one large entry of a row is not rounded to bf16
+  // device-resident scalars (no host sync to read a parameter or the upstream gradient): alpha = *alpha_dev, coef *= *coef_dev
+  const float* alpha_dev;
+  const float* coef_dev;
+  void* D;                // EPI_SOFTGRAD output of THIS problem (grouped launches carry two problems, see GemmParams::n_prob)
 };
 
 enum { EPI_STD = 0, EPI_LSE = 1, EPI_SOFTGRAD = 2, EPI_RANK = 3 };
@@ -104,6 +109,10 @@ struct GemmParams {
   uint32_t wait_ns;  // > 0: epilogue warps wait for the accumulator with a suspending try_wait (hint in ns) instead of spinning
   EpiParams epi;
   ContrastParams con;
+  // grouped launch of the contrastive epilogues: problem 1 (same M, N, K, pitches of D) has its own operands (tmA2 / tmB2) and ContrastParams;
+  // its tiles follow problem 0's in the persistent schedule, so one launch fills the SMs where two half-empty waves ran before
+  int32_t n_prob;
+  ContrastParams con2;
 };
 
 // Full epilogue on 8 consecutive columns of one row (n % 8 == 0). Shared by the GEMM epilogue warps and the split-K
@@ -272,6 +281,7 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p) {
   TileCoord c;
   int64_t per_split = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  if (t >= per_split * p.splits) t -= per_split * p.splits;  // second problem of a grouped launch: same tile grid
   c.split = static_cast<int32_t>(t / per_split);
   int64_t rem = t - c.split * per_split;
   c.m_blk = static_cast<int32_t>(rem / p.n_tiles);
@@ -285,7 +295,8 @@ __device__ __forceinline__ TileCoord decode_tile(int64_t t, const GemmParams& p)
 // FL == -1 keeps them as runtime values (any combination, edge flavours).
 template <bool A_MN, bool B_MN, int EPI, int CG, int FL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+contrast_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using PC = PairCfg<CG>;
   constexpr int STAGES = PC::NSTAGES;           // shadows the 1-CTA constants inside this kernel
   constexpr int STAGE_BYTES = PC::STAGE;
@@ -328,7 +339,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int64_t tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;  // a pair walks the macro-tile list together
 
-  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int64_t tiles_per_prob = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int64_t total_tiles = tiles_per_prob * (EPI == EPI_STD ? 1 : p.n_prob);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -336,6 +348,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
+      const bool second = EPI != EPI_STD && t >= tiles_per_prob;
+      const CUtensorMap* const pA = second ? &tmA2 : &tmA;
+      const CUtensorMap* const pB = second ? &tmB2 : &tmB;
       const int32_t m0 = tc.m_blk * (BM * CG) + static_cast<int32_t>(cta_rank) * BM;
       const int32_t n0 = tc.n_blk * BN + static_cast<int32_t>(cta_rank) * PC::BN_CTA;  // this CTA's share of the B tile
       for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
@@ -347,16 +362,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
             if constexpr (!A_MN) {
-              tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
+              tma_load_2d(pA, &full_bar[stage], sa, k0, m0);
             } else {
 #pragma unroll
-              for (int s = 0; s < BM / 64; ++s) tma_load_2d(&tmA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
+              for (int s = 0; s < BM / 64; ++s) tma_load_2d(pA, &full_bar[stage], sa + s * SLAB_BYTES, m0 + 64 * s, k0);
             }
             if constexpr (!B_MN) {
-              tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+              tma_load_2d(pB, &full_bar[stage], sb, k0, n0);
             } else {
 #pragma unroll
-              for (int s = 0; s < BN / 64; ++s) tma_load_2d(&tmB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
+              for (int s = 0; s < BN / 64; ++s) tma_load_2d(pB, &full_bar[stage], sb + s * SLAB_BYTES, n0 + 64 * s, k0);
             }
           } else {
             // both CTAs land their bytes on the LEADER's full barrier; only the leader arms it (for the pair's total)
@@ -433,6 +448,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int64_t t = tile0; t < total_tiles; t += tile_stride) {
       const TileCoord tc = decode_tile(t, p);
+      const ContrastParams& con = (EPI != EPI_STD && t >= tiles_per_prob) ? p.con2 : p.con;
+      const float alpha = (EPI != EPI_STD && con.alpha_dev != nullptr) ? *con.alpha_dev : p.epi.alpha;
       const int64_t m_cta = static_cast<int64_t>(tc.m_blk) * (BM * CG) + cta_rank * BM;  // first row of this CTA's 128
       const int64_t m = m_cta + quarter * 32 + lane;
       const int64_t n0 = static_cast<int64_t>(tc.n_blk) * BN;
@@ -543,7 +560,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else if constexpr (EPI == EPI_LSE) {
         // online (max, sum-exp) over this tile's columns of row m; the diagonal logit is captured on the way
         float mx = -INFINITY, sm = 0.f;
-        const int64_t dcol = m + p.con.diag_off;
+        const int64_t dcol = m + con.diag_off;
 #pragma unroll 1
         for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
@@ -554,7 +571,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float cm = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float z = nb + j < p.N ? __uint_as_float(r[j]) * p.epi.alpha : -INFINITY;
+              const float z = nb + j < p.N ? __uint_as_float(r[j]) * alpha : -INFINITY;
               r[j] = __float_as_uint(z);
               cm = fmaxf(cm, z);
             }
@@ -567,18 +584,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (m < p.M && dcol >= nb && dcol < nb + 32 && dcol < p.N) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (nb + j == dcol) p.con.diag[m] = __uint_as_float(r[j]);
+                if (nb + j == dcol) con.diag[m] = __uint_as_float(r[j]);
             }
           }
         }
         if (m < p.M) {
-          p.con.part_max[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = mx;
-          p.con.part_sum[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = sm;
+          con.part_max[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = mx;
+          con.part_sum[m * (EPI_PARTS * p.n_tiles) + EPI_PARTS * tc.n_blk + cpart] = sm;
         }
       } else if constexpr (EPI == EPI_RANK) {
         // retrieval rank of the positive: how many logits of row m beat the reference logit (strictly), the positive itself excluded
-        const float ref = m < p.M ? p.con.row_lse[m] : INFINITY;
-        const int64_t dcol = m < p.M ? (p.con.gt_col != nullptr ? static_cast<int64_t>(p.con.gt_col[m]) : m + p.con.diag_off) : -1;
+        const float ref = m < p.M ? con.row_lse[m] : INFINITY;
+        const int64_t dcol = m < p.M ? (con.gt_col != nullptr ? static_cast<int64_t>(con.gt_col[m]) : m + con.diag_off) : -1;
         int cnt = 0;
 #pragma unroll 1
         for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
@@ -589,15 +606,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (nb < p.N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              cnt += (nb + j < p.N && nb + j != dcol && __uint_as_float(r[j]) * p.epi.alpha > ref) ? 1 : 0;
+              cnt += (nb + j < p.N && nb + j != dcol && __uint_as_float(r[j]) * alpha > ref) ? 1 : 0;
           }
         }
-        if (m < p.M && cnt) atomicAdd(p.con.rank_out + m, cnt);
+        if (m < p.M && cnt) atomicAdd(con.rank_out + m, cnt);
       } else {
-        const float lse = m < p.M ? p.con.row_lse[m] : 0.f;
-        const int64_t dcol = m + p.con.diag_off;
+        const float lse = m < p.M ? con.row_lse[m] : 0.f;
+        const int64_t dcol = m + con.diag_off;
+        const float coef = con.coef_dev != nullptr ? con.coef * *con.coef_dev : con.coef;
+        const bool two_sided = con.col_lse != nullptr;
         float ds_acc = 0.f;
-        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.epi.D) + m * p.epi.ldd;
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(con.D) + m * p.epi.ldd;
 #pragma unroll 1
         for (int c = cpart; c < EPI_CHUNKS; c += EPI_PARTS) {
           uint32_t r[32];
@@ -611,12 +630,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float z = __uint_as_float(r[g * 8 + j]) * p.epi.alpha;
+                  const float z = __uint_as_float(r[g * 8 + j]) * alpha;
                   const bool on_diag = (n + j == dcol);
-                  float gz = p.con.coef * (__expf(z - lse) - (on_diag ? p.con.diag_sub : 0.f));
-                  if ((on_diag && p.con.diag_zero) || n + j >= p.con.n_valid) gz = 0.f;
+                  float gz;
+                  if (two_sided) {
+                    // this logit is also entry (n, m) of the transposed block, normalised there by col_lse[n]: both softmax terms at once
+                    const bool valid = n + j < con.n_valid;
+                    const float er = (on_diag && con.row_diag_zero) ? 0.f : __expf(z - lse);
+                    const float ec = (!valid || (on_diag && con.col_diag_zero)) ? 0.f : __expf(z - __ldg(con.col_lse + (valid ? n + j : 0)));
+                    gz = coef * (er + ec - (on_diag ? con.diag_sub : 0.f));
+                  } else {
+                    gz = coef * (__expf(z - lse) - (on_diag ? con.diag_sub : 0.f));
+                  }
+                  if ((on_diag && con.diag_zero) || n + j >= con.n_valid) gz = 0.f;
                   ds_acc += gz * z;
-                  v[j] = gz * p.epi.alpha;  // dL/d<a_m, b_n>
+                  if (two_sided && con.diag_exact && on_diag) gz += coef * con.diag_sub;
+                  v[j] = gz * alpha;  // dL/d<a_m, b_n>
                 }
                 uint4 o;
                 o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -626,9 +655,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (p.con.dscale != nullptr) {
+        if (con.dscale != nullptr) {
           ds_acc = warp_sum(ds_acc);
-          if (lane == 0) atomicAdd(p.con.dscale, ds_acc);
+          if (lane == 0) atomicAdd(con.dscale, ds_acc);
         }
       }
       tc_fence_before();
@@ -648,30 +677,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// split-K reduction + full epilogue; one thread per 8 output columns
-__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __restrict__ partial, int64_t M, int64_t N,
-                                                                  int32_t splits, EpiParams e) {
-  const int64_t n8 = N / 8;
-  const int64_t total = M * n8;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t m = i / n8;
-    const int64_t n = (i - m * n8) * 8;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < splits; ++s) {
-      const float* src = partial + (static_cast<int64_t>(s) * M + m) * N + n;
-      float4 a = *reinterpret_cast<const float4*>(src);
-      float4 b = *reinterpret_cast<const float4*>(src + 4);
-      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-      v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-    }
-    epi_apply8(v, m, n, e);
-  }
-}
-
 template <bool A_MN, bool B_MN, int EPI, int CG, int FL = -1>
-static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, EPI, CG, FL>;
+static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream, const CUtensorMap* tmA2 = nullptr,
+                          const CUtensorMap* tmB2 = nullptr) {
+  auto kern = contrast_pair_kernel<A_MN, B_MN, EPI, CG, FL>;
   constexpr int smem = PairCfg<CG>::SMEM;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
@@ -682,7 +691,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     }
     attr_set = true;
   }
-  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits;
+  const int64_t total_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.splits * (EPI == EPI_STD || p.n_prob < 1 ? 1 : p.n_prob);
   const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs
   const int grid = static_cast<int>(total_tiles < units ? total_tiles : units) * CG;
   cudaLaunchConfig_t cfg = {};
@@ -697,207 +706,33 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2 ? *tmA2 : tmA, tmB2 ? *tmB2 : tmB, p);
   if (e != cudaSuccess) {
-    set_last_error("gemm_tcgen05_kernel<CG=%d> launch: %s", CG, cudaGetErrorString(e));
+    set_last_error("contrast_pair_kernel<CG=%d> launch: %s", CG, cudaGetErrorString(e));
     return B200MM_ERR_LAUNCH;
   }
-  return check_launch("gemm_tcgen05_kernel");
+  return check_launch("contrast_pair_kernel");
 }
 
 template <bool A_MN, bool B_MN, int EPI = EPI_STD>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  return launch_gemm_cg<A_MN, B_MN, EPI, 1>(tmA, tmB, p, stream);
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream, const CUtensorMap* tmA2 = nullptr,
+                       const CUtensorMap* tmB2 = nullptr) {
+  return launch_gemm_cg<A_MN, B_MN, EPI, 1>(tmA, tmB, p, stream, tmA2, tmB2);
 }
 
-// Merge per-tile (max, sum-exp) partials of up to two logit blocks into one log-sum-exp per row.
-//   lse[m] = log( sum_t sumA[m,t] e^{maxA[m,t]} (+ sum_t sumB[m,t] e^{maxB[m,t]}) (- e^{diag[m]} if sub_diag) )
-//   loss_sum += sum_m (lse[m] - diag[m])            (fp32 atomic; caller zero-fills)
-// sub_diag < 0 ADDS e^{diag[m]} instead (MoCo: LSE over the positive logit and the queue negatives, moco_utils.py:71-81).
-// sub_diag implements MIL-NCE's union {video_j·all texts} ∪ {text_j·videos k != j}, where the positive logit would
-// otherwise be counted twice (prj/base_vtp/roi_univl/univl/model/univl_video_ret.py:146-197).
-// One WARP per row: lanes stride over the row's tile partials (coalesced), shuffles reduce max and sum; one loss atomic per CTA.
-// (The first version used one thread per row: strided reads and 4 CTAs for 1024 rows — 43 us per call under ncu, more than the
-// LSE GEMM it follows; profiles/r01h_contrast_bench.log.)
-__global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ maxA, const float* __restrict__ sumA, int32_t tA,
-                                                        const float* __restrict__ maxB, const float* __restrict__ sumB, int32_t tB,
-                                                        const float* __restrict__ diag, int32_t sub_diag, float* __restrict__ lse,
-                                                        float* __restrict__ loss_sum, int64_t M) {
-  __shared__ float cta_term[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t m = blockIdx.x * 8ll + warp;
-  float term = 0.f;
-  if (m < M) {  // warp-uniform
-    const float* mA = maxA + m * tA;
-    const float* sA = sumA + m * tA;
-    const float* mB = tB > 0 ? maxB + m * tB : nullptr;
-    const float* sB = tB > 0 ? sumB + m * tB : nullptr;
-    float mx = -INFINITY;
-    for (int t = lane; t < tA; t += 32) mx = fmaxf(mx, mA[t]);
-    for (int t = lane; t < tB; t += 32) mx = fmaxf(mx, mB[t]);
-    mx = warp_max(mx);
-    float sm = 0.f;
-    for (int t = lane; t < tA; t += 32) sm += sA[t] * __expf(mA[t] - mx);
-    for (int t = lane; t < tB; t += 32) sm += sB[t] * __expf(mB[t] - mx);
-    sm = warp_sum(sm);
-    const float d = diag[m];
-    if (sub_diag > 0) {
-      sm -= __expf(d - mx);
-    } else if (sub_diag < 0) {  // the extra logit d joins the log-sum-exp (MoCo: positive + queue negatives)
-      const float nm = fmaxf(mx, d);
-      sm = sm * __expf(mx - nm) + __expf(d - nm);
-      mx = nm;
-    }
-    const float l = mx + __logf(sm);
-    if (lane == 0) lse[m] = l;
-    term = l - d;
-  }
-  if (lane == 0) cta_term[warp] = term;
-  __syncthreads();
-  if (threadIdx.x == 0 && loss_sum != nullptr) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += cta_term[i];
-    atomicAdd(loss_sum, s);
-  }
-}
-
+}  // namespace pair
 }  // namespace b200mm
 
 using namespace b200mm;
+using namespace b200mm::pair;
 
-extern "C" int64_t b200mm_gemm_workspace_bytes(int64_t M, int64_t N, int32_t splits) {
-  return splits > 1 ? static_cast<int64_t>(splits) * M * N * 4 : 0;
-}
-
-extern "C" int b200mm_gemm_bf16(const b200mm_gemm_args* a, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  B200MM_REQUIRE(a != nullptr, B200MM_ERR_SHAPE, "gemm: null args");
-  B200MM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, B200MM_ERR_SHAPE, "gemm: M=%lld N=%lld K=%lld must be positive",
-                 (long long)a->M, (long long)a->N, (long long)a->K);
-  B200MM_REQUIRE(a->N % 8 == 0, B200MM_ERR_SHAPE, "gemm: N=%lld must be a multiple of 8", (long long)a->N);
-  B200MM_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), B200MM_ERR_SHAPE, "gemm: dims exceed int32");
-  B200MM_REQUIRE(a->A && a->B && a->D, B200MM_ERR_SHAPE, "gemm: null operand");
-  B200MM_REQUIRE(a->ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, B200MM_ERR_ALIGN,
-                 "gemm: D must be 16B aligned with pitch %% 8 == 0 (ldd=%lld)", (long long)a->ldd);
-  B200MM_REQUIRE(!a->residual || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0), B200MM_ERR_ALIGN,
-                 "gemm: residual alignment");
-  B200MM_REQUIRE(!a->dact_in || (a->ld_dact % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dact_in) & 15) == 0), B200MM_ERR_ALIGN,
-                 "gemm: dact_in alignment");
-  B200MM_REQUIRE(!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, B200MM_ERR_ALIGN, "gemm: bias alignment");
-  B200MM_REQUIRE(!a->aux_out || (reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0, B200MM_ERR_ALIGN, "gemm: aux_out alignment");
-  B200MM_REQUIRE(a->act >= 0 && a->act <= 2, B200MM_ERR_SHAPE, "gemm: unknown activation %d", a->act);
-  B200MM_REQUIRE(!(a->dact_in && a->residual), B200MM_ERR_SHAPE, "gemm: dact_in and residual are mutually exclusive");
-  B200MM_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, B200MM_ERR_SHAPE, "gemm: drop_p=%f must be in [0, 1)", a->drop_p);
-  B200MM_REQUIRE(!(a->drop_p > 0.f && (a->dact_in || a->aux_out)), B200MM_ERR_SHAPE, "gemm: dropout cannot be combined with dact_in / aux_out");
-
-  // CTA-pair (cta_group::2) kernels for everything that has at least one 256-row macro-tile per pair; B200MM_GEMM_CG=1 forces
-  // the single-CTA kernels
-  static const int cg_env = getenv("B200MM_GEMM_CG") ? atoi(getenv("B200MM_GEMM_CG")) : 2;
-  const int cg = (cg_env == 2 && a->M > BM) ? 2 : 1;
-  GemmParams p;
-  p.M = a->M; p.N = a->N; p.K = a->K;
-  p.m_tiles = static_cast<int32_t>(ceil_div(a->M, BM * cg));
-  p.n_tiles = static_cast<int32_t>(ceil_div(a->N, BN));
-  p.kb_total = static_cast<int32_t>(ceil_div(a->K, BK));
-  int32_t splits = a->splits < 1 ? 1 : a->splits;
-  if (splits > p.kb_total) splits = p.kb_total;
-  p.kb_per_split = static_cast<int32_t>(ceil_div(p.kb_total, splits));
-  splits = static_cast<int32_t>(ceil_div(p.kb_total, p.kb_per_split));  // no empty split
-  p.splits = splits;
-  p.partial = nullptr;
-  if (splits > 1) {
-    int64_t need = b200mm_gemm_workspace_bytes(a->M, a->N, splits);
-    B200MM_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, B200MM_ERR_SHAPE,
-                   "gemm: split-K needs %lld workspace bytes, got %lld", (long long)need, (long long)a->workspace_bytes);
-    B200MM_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, B200MM_ERR_ALIGN, "gemm: workspace alignment");
-    p.partial = reinterpret_cast<float*>(a->workspace);
-  }
-  p.mn_lbo = SLAB_BYTES; p.mn_sbo = 1024; p.k_lbo = 16; p.k_sbo = 1024;
-  p.wait_ns = gemm_wait_ns();
-  if (const char* dbg = getenv("B200MM_DBG_DESC")) {  // bring-up only: "mn_lbo,mn_sbo,k_lbo,k_sbo" in bytes
-    unsigned v[4];
-    if (sscanf(dbg, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]) == 4) { p.mn_lbo = v[0]; p.mn_sbo = v[1]; p.k_lbo = v[2]; p.k_sbo = v[3]; }
-  }
-  p.epi.D = a->D; p.epi.ldd = a->ldd; p.epi.d_f32 = a->d_f32; p.epi.alpha = a->alpha;
-  p.epi.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
-  p.epi.act = a->act;
-  p.epi.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
-  p.epi.dact_in = reinterpret_cast<const __nv_bfloat16*>(a->dact_in);
-  p.epi.ld_dact = a->ld_dact;
-  p.epi.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
-  p.epi.ldr = a->ldr;
-  p.epi.drop_thr = a->drop_p > 0.f ? drop_threshold(a->drop_p) : 0u;
-  p.epi.drop_inv_keep = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  p.epi.drop_seed = a->drop_seed;
-
-  CUtensorMap tmA, tmB;
-  int rc;
-  if (!a->a_mn) rc = make_tmap_2d_bf16(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
-  else          rc = make_tmap_2d_bf16(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
-  if (rc) return rc;
-  if (!a->b_mn) rc = make_tmap_2d_bf16(&tmB, a->B, a->K, a->N, a->ldb, BK, BN / cg);  // a pair's CTAs each load half of the N rows
-  else          rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
-  if (rc) return rc;
-
-  if (cg == 2) {
-    // flavours of the training step get kernels with the epilogue flags baked in (no per-element flag branches); anything else
-    // (and split-K partial tiles) runs the runtime-flag kernel
-    const int fl = splits > 1 ? -1
-                              : flavor_bits(a->bias != nullptr, a->aux_out != nullptr, a->residual != nullptr, a->dact_in != nullptr,
-                                            a->d_f32 != 0, a->alpha != 1.f, a->act, p.epi.drop_thr != 0u);
-    bool done = true;
-#define B200MM_TRY(AMN, BMN, ...)                                                                   \
-  else if (a->a_mn == AMN && a->b_mn == BMN && fl == flavor_bits(__VA_ARGS__))                      \
-    rc = launch_gemm_cg<AMN != 0, BMN != 0, EPI_STD, 2, flavor_bits(__VA_ARGS__)>(tmA, tmB, p, stream);
-    if (fl < 0) done = false;
-    //          bias   aux    res    dact   f32    scale  act
-    B200MM_TRY(0, 0, true, false, false, false, false, false, B200MM_ACT_NONE)       // qkv / dense projections
-    B200MM_TRY(0, 0, true, false, true, false, false, false, B200MM_ACT_NONE)        // out_proj / c_proj (+ residual)
-    B200MM_TRY(0, 0, true, false, true, false, false, false, B200MM_ACT_NONE, true)  // BERT self-output / output: dropout(dense) + residual
-    B200MM_TRY(0, 0, true, true, false, false, false, false, B200MM_ACT_QUICKGELU)   // ViT c_fc
-    B200MM_TRY(0, 0, true, true, false, false, false, false, B200MM_ACT_GELU_ERF)    // BERT intermediate
-    B200MM_TRY(0, 0, false, false, false, false, false, false, B200MM_ACT_NONE)      // patch embedding
-    B200MM_TRY(0, 1, false, false, false, false, false, false, B200MM_ACT_NONE)      // plain dgrad
-    B200MM_TRY(0, 1, false, false, true, false, false, false, B200MM_ACT_NONE)       // dgrad + residual-branch gradient
-    B200MM_TRY(0, 1, false, false, false, true, false, false, B200MM_ACT_QUICKGELU)  // dgrad through QuickGELU
-    B200MM_TRY(0, 1, false, false, false, true, false, false, B200MM_ACT_GELU_ERF)   // dgrad through erf-GELU
-    B200MM_TRY(0, 1, false, true, false, true, false, false, B200MM_ACT_QUICKGELU)   // ... also emitting act(u) (activation recompute)
-    B200MM_TRY(0, 1, false, true, false, true, false, false, B200MM_ACT_GELU_ERF)
-    else done = false;
-#undef B200MM_TRY
-    if (done) {
-    } else if (!a->a_mn && !a->b_mn) rc = launch_gemm_cg<false, false, EPI_STD, 2>(tmA, tmB, p, stream);
-    else if (!a->a_mn && a->b_mn) rc = launch_gemm_cg<false, true, EPI_STD, 2>(tmA, tmB, p, stream);
-    else if (a->a_mn && !a->b_mn) rc = launch_gemm_cg<true, false, EPI_STD, 2>(tmA, tmB, p, stream);
-    else rc = launch_gemm_cg<true, true, EPI_STD, 2>(tmA, tmB, p, stream);
-  } else {
-    if (!a->a_mn && !a->b_mn) rc = launch_gemm<false, false>(tmA, tmB, p, stream);
-    else if (!a->a_mn && a->b_mn) rc = launch_gemm<false, true>(tmA, tmB, p, stream);
-    else if (a->a_mn && !a->b_mn) rc = launch_gemm<true, false>(tmA, tmB, p, stream);
-    else rc = launch_gemm<true, true>(tmA, tmB, p, stream);
-  }
-  if (rc) return rc;
-
-  if (splits > 1) {
-    const int64_t total = a->M * (a->N / 8);
-    int blocks = static_cast<int>(ceil_div(total, 256) < 148 * 8 ? ceil_div(total, 256) : 148 * 8);
-    gemm_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, a->M, a->N, splits, p.epi);
-    return check_launch("gemm_splitk_reduce_kernel");
-  }
-  return B200MM_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// contrastive similarity + log-softmax pieces (K8). Logits z[m,n] = alpha * <a_m, b_n> are produced tile by tile in
-// TMEM and consumed in the epilogue; the [M, N] logit matrix is never written to HBM in forward.
-// ---------------------------------------------------------------------------------------------------------------
 static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const void* a, int64_t lda, const void* b, int64_t ldb,
                        int32_t b_mn, int64_t M, int64_t N, int64_t K, float alpha) {
   B200MM_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), B200MM_ERR_SHAPE,
                  "contrast: M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   B200MM_REQUIRE(a && b, B200MM_ERR_SHAPE, "contrast: null operand");
   p = GemmParams{};
+  p.n_prob = 1;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = static_cast<int32_t>(ceil_div(M, BM));
   p.n_tiles = static_cast<int32_t>(ceil_div(N, BN));
@@ -914,55 +749,53 @@ static int setup_plain(GemmParams& p, CUtensorMap& tmA, CUtensorMap& tmB, const 
   return make_tmap_2d_bf16(&tmB, b, N, K, ldb, 64, BK);  // b stored [K, N] row-major (e.g. the MoCo queue [dim, K_queue])
 }
 
-extern "C" int32_t b200mm_contrast_num_tiles(int64_t N) { return static_cast<int32_t>(EPI_PARTS * ceil_div(N, BN)); }  // partials per row
-
-extern "C" int b200mm_contrast_lse_partials(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N,
-                                            int64_t K, float alpha, int64_t diag_off, float* part_max, float* part_sum, float* diag,
-                                            void* stream) {
-  GemmParams p;
-  CUtensorMap tmA, tmB;
-  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, b_mn, M, N, K, alpha);
+// ---- grouped (two problems per launch) forms for symmetric losses: problem 0 = rows a0 x columns b0, problem 1 = rows a1 x columns b1
+static int setup_pair(GemmParams& p, CUtensorMap (&tm)[4], const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1,
+                      const void* b1, int64_t ldb1, int64_t M, int64_t N, int64_t K, float alpha) {
+  int rc = setup_plain(p, tm[0], tm[1], a0, lda0, b0, ldb0, 0, M, N, K, alpha);
   if (rc) return rc;
-  B200MM_REQUIRE(part_max && part_sum && diag, B200MM_ERR_SHAPE, "contrast_lse_partials: null output");
-  p.con.part_max = part_max; p.con.part_sum = part_sum; p.con.diag = diag; p.con.diag_off = diag_off;
-  if (b_mn) return launch_gemm<false, true, EPI_LSE>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
-  return launch_gemm<false, false, EPI_LSE>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
-}
-
-extern "C" int b200mm_contrast_lse_merge(const float* maxA, const float* sumA, int32_t tilesA, const float* maxB, const float* sumB,
-                                         int32_t tilesB, const float* diag, int32_t sub_diag, float* lse, float* loss_sum, int64_t M,
-                                         void* stream) {
-  B200MM_REQUIRE(M > 0 && maxA && sumA && diag && lse && tilesA > 0 && (tilesB == 0 || (maxB && sumB)), B200MM_ERR_SHAPE,
-                 "contrast_lse_merge: bad arguments");
-  lse_merge_kernel<<<static_cast<int>(ceil_div(M, 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      maxA, sumA, tilesA, maxB, sumB, tilesB, diag, sub_diag, lse, loss_sum, M);
-  return check_launch("lse_merge_kernel");
-}
-
-extern "C" int b200mm_contrast_softgrad(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
-                                        int64_t n_valid, float alpha, int64_t diag_off, const float* row_lse, float coef,
-                                        float diag_sub, int32_t diag_zero, void* G, int64_t ldg, float* dscale, void* stream) {
-  GemmParams p;
-  CUtensorMap tmA, tmB;
-  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, b_mn, M, N, K, alpha);
+  GemmParams q;
+  rc = setup_plain(q, tm[2], tm[3], a1, lda1, b1, ldb1, 0, M, N, K, alpha);
   if (rc) return rc;
-  B200MM_REQUIRE(row_lse && G && N % 8 == 0 && ldg % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, B200MM_ERR_ALIGN,
-                 "contrast_softgrad: G must be 16B aligned, N and ldg multiples of 8");
-  p.epi.D = G; p.epi.ldd = ldg;
-  p.con.row_lse = row_lse; p.con.coef = coef; p.con.diag_sub = diag_sub; p.con.diag_zero = diag_zero;
-  p.con.diag_off = diag_off; p.con.dscale = dscale; p.con.n_valid = n_valid;
-  if (b_mn) return launch_gemm<false, true, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
-  return launch_gemm<false, false, EPI_SOFTGRAD>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+  p.n_prob = 2;
+  return B200MM_OK;
 }
 
-extern "C" int b200mm_contrast_rank(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t b_mn, int64_t M, int64_t N, int64_t K,
-                                    float alpha, int64_t diag_off, const int32_t* gt_col, const float* ref, int32_t* rank_out, void* stream) {
+extern "C" int b200mm_contrast_lse_partials_pair(const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1,
+                                                 const void* b1, int64_t ldb1, int64_t M, int64_t N, int64_t K, float alpha,
+                                                 const float* alpha_dev, int64_t diag_off, float* part_max0, float* part_sum0, float* diag0,
+                                                 float* part_max1, float* part_sum1, float* diag1, void* stream) {
   GemmParams p;
-  CUtensorMap tmA, tmB;
-  int rc = setup_plain(p, tmA, tmB, a, lda, b, ldb, b_mn, M, N, K, alpha);
+  CUtensorMap tm[4];
+  int rc = setup_pair(p, tm, a0, lda0, b0, ldb0, a1, lda1, b1, ldb1, M, N, K, alpha);
   if (rc) return rc;
-  B200MM_REQUIRE(ref && rank_out, B200MM_ERR_SHAPE, "contrast_rank: null reference / output");
-  p.con.row_lse = ref; p.con.rank_out = rank_out; p.con.gt_col = gt_col; p.con.diag_off = diag_off;
-  if (b_mn) return launch_gemm<false, true, EPI_RANK>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
-  return launch_gemm<false, false, EPI_RANK>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+  B200MM_REQUIRE(part_max0 && part_sum0 && diag0 && part_max1 && part_sum1 && diag1, B200MM_ERR_SHAPE, "contrast_lse_partials_pair: null output");
+  p.con.part_max = part_max0; p.con.part_sum = part_sum0; p.con.diag = diag0; p.con.diag_off = diag_off; p.con.alpha_dev = alpha_dev;
+  p.con2 = p.con;
+  p.con2.part_max = part_max1; p.con2.part_sum = part_sum1; p.con2.diag = diag1;
+  return launch_gemm<false, false, EPI_LSE>(tm[0], tm[1], p, reinterpret_cast<cudaStream_t>(stream), &tm[2], &tm[3]);
 }
+
+extern "C" int b200mm_contrast_softgrad_pair(const void* a0, int64_t lda0, const void* b0, int64_t ldb0, const void* a1, int64_t lda1, const void* b1,
+                                             int64_t ldb1, int64_t M, int64_t N, int64_t K, int64_t n_valid, float alpha, const float* alpha_dev,
+                                             int64_t diag_off, const float* row_lse0, const float* col_lse0, const float* row_lse1,
+                                             const float* col_lse1, float coef, const float* coef_dev, float diag_sub, int32_t row_diag_zero0,
+                                             int32_t col_diag_zero0, int32_t row_diag_zero1, int32_t col_diag_zero1, void* G0, void* G1, int64_t ldg,
+                                             float* dscale, void* stream) {
+  GemmParams p;
+  CUtensorMap tm[4];
+  int rc = setup_pair(p, tm, a0, lda0, b0, ldb0, a1, lda1, b1, ldb1, M, N, K, alpha);
+  if (rc) return rc;
+  B200MM_REQUIRE(row_lse0 && col_lse0 && row_lse1 && col_lse1 && G0 && G1 && N % 8 == 0 && ldg % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(G0) & 15) == 0 && (reinterpret_cast<uintptr_t>(G1) & 15) == 0,
+                 B200MM_ERR_ALIGN, "contrast_softgrad_pair: row / column LSEs required; G 16B aligned, N and ldg multiples of 8");
+  p.epi.D = G0; p.epi.ldd = ldg;
+  p.con.D = G0; p.con.row_lse = row_lse0; p.con.col_lse = col_lse0; p.con.coef = coef; p.con.coef_dev = coef_dev; p.con.diag_sub = diag_sub;
+  p.con.row_diag_zero = row_diag_zero0; p.con.col_diag_zero = col_diag_zero0; p.con.diag_off = diag_off; p.con.dscale = dscale;
+  p.con.n_valid = n_valid; p.con.alpha_dev = alpha_dev; p.con.diag_exact = 1;
+  p.con2 = p.con;
+  p.con2.D = G1; p.con2.row_lse = row_lse1; p.con2.col_lse = col_lse1; p.con2.row_diag_zero = row_diag_zero1; p.con2.col_diag_zero = col_diag_zero1;
+  p.con2.dscale = nullptr;  // every logit pair is visited by both problems: the log-temperature gradient is taken from problem 0 only
+  return launch_gemm<false, false, EPI_SOFTGRAD>(tm[0], tm[1], p, reinterpret_cast<cudaStream_t>(stream), &tm[2], &tm[3]);
+}
+
