@@ -156,7 +156,7 @@ class _ContrastiveTwoSidedFn(Function):
     """The same two losses as _ContrastiveFn (same arguments, same value), restructured — the OPT-IN backend "two_sided"
     (set_backend / B200MM_CONTRASTIVE): written at the end of round 2 after the round's GPU budget was spent, verified on the CPU against
     the oracle over the emulated kernels (tests/test_contrastive_two_sided_cpu.py) but NOT yet run on hardware; its GPU checks are
-    tests/test_zz_contrastive_two_sided_gpu.py (expected-to-pass, non-strict). The default stays the hardware-verified _ContrastiveFn.
+    tests/test_zz_contrastive_two_sided_gpu.py (expected-to-pass, non-strict). The default stays _ContrastiveFn on the hardware-verified kernels.
 
     Per step and rank: ONE all-gather of the embeddings ([B, 2E] rows) and one of the row log-sum-exps (2 B floats); no gradient exchange.
     Every logit z[i, t] = s <a_i, b_t> is an entry of block A on the rank that owns row i AND of block Bt on the rank that owns row t; with the
@@ -292,7 +292,7 @@ _backend = os.environ.get("B200MM_CONTRASTIVE", "gathered_grad")
 
 
 def set_backend(name):
-    """"gathered_grad" (default, hardware-verified): softmax-gradient tiles per block, gradients of the gathered rows reduce-scattered home.
+    """"gathered_grad" (default, hardware-verified kernels): softmax-gradient tiles per block, gradients of the gathered rows reduce-scattered home.
     "two_sided": grouped launches, two-sided gradient tiles, no gradient exchange (see _ContrastiveTwoSidedFn)."""
     global _backend
     if name not in _BACKENDS:
