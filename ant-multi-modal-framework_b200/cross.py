@@ -103,24 +103,27 @@ def mil_nce_matrix_loss(sim_matrix, weight_vector=None):
 
 
 def hard_mining_indices(l1_simi, beg_idx, bsz, method="top_k"):
-    """The reference's negative selection, row by row with the same torch.topk calls (univl_video_ret.py:107-131): returns int64
-    [bsz, bsz] global video indices, slot i of row i = the positive beg_idx + i. `l1_simi` is left untouched."""
-    out = torch.empty((bsz, bsz), dtype=torch.long, device=l1_simi.device)
-    for i in range(bsz):
-        raw = beg_idx + i
-        row = l1_simi[raw].clone()
-        if method == "top_k":
-            row[raw] -= 100.0
-            _, chosen = torch.topk(row, bsz, sorted=False)
-        elif method == "nearliest":
-            row = (row - row[raw]).abs()
-            row[raw] = 100.0
-            _, chosen = torch.topk(row, bsz, sorted=False, largest=False)
-        else:
-            raise ValueError(f"re_sample_method {method!r}: expected 'top_k' or 'nearliest'")
-        out[i] = chosen
-        out[i, i] = raw
-    return out
+    """The reference's negative selection (univl_video_ret.py:107-131) for all `bsz` local rows in ONE batched `torch.topk` instead of one
+    call per row: returns int64 [bsz, bsz] global video indices, slot i of row i = the positive beg_idx + i. `l1_simi` is left untouched.
+    The reference calls `torch.topk(row, bsz, sorted=False)` row by row and overwrites slot i of ITS result order with the positive, so the
+    order topk returns decides which negative is dropped; the batched call selects per row with the same routine, and its rows are
+    element-for-element equal to the per-row calls (asserted against the row-by-row restatement of the oracle in
+    tests/test_cross_host_cpu.py and tests/test_host_properties_cpu.py on every case they run)."""
+    idx = torch.arange(bsz, device=l1_simi.device)
+    raw = beg_idx + idx
+    rows = l1_simi[beg_idx:beg_idx + bsz].clone()
+    if method == "top_k":
+        rows[idx, raw] -= 100.0
+        _, chosen = torch.topk(rows, bsz, dim=1, sorted=False)
+    elif method == "nearliest":
+        rows = (rows - rows[idx, raw][:, None]).abs()
+        rows[idx, raw] = 100.0
+        _, chosen = torch.topk(rows, bsz, dim=1, sorted=False, largest=False)
+    else:
+        raise ValueError(f"re_sample_method {method!r}: expected 'top_k' or 'nearliest'")
+    chosen = chosen.clone()
+    chosen[idx, idx] = raw
+    return chosen
 
 
 def hard_mining_weights(l1_diag, method="top_k"):

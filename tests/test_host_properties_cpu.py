@@ -3,6 +3,8 @@ XPOS tables against the live reference module, the hard-negative selection, spli
 import pytest
 import torch
 
+from oracle import restated
+
 from oracle import ref_loader
 
 
@@ -61,6 +63,8 @@ def test_hard_mining_indices_properties(method):
             score = row if method == "top_k" else -(row - l1[raw, raw]).abs()
             kth = torch.topk(score, bsz).values[-1]
             assert all(score[n] >= kth for n in negs)                               # every negative is among the bsz hardest
+        # the batched selection is element-for-element the reference's row-by-row torch.topk loop (slot order included)
+        assert torch.equal(ch, restated.hard_mining_indices(l1, rank * bsz, bsz, method))
 
 
 def test_pick_splits_planning(monkeypatch):
