@@ -37,10 +37,29 @@ def _world(group=None):
     return 0, 1
 
 
+def _check_equal_rows(x, group):
+    """The fused losses shard B rows per rank with offset rank * B (like the reference's hard mining: beg_idx = rank * bsz,
+    univl_video_ret.py:96-106) — every rank must hold the same number of pairs (DistributedSampler does that). A rank with a different row
+    count would corrupt or hang the all-gather; the per-step guard costs one int all-gather and a host read, so it is opt-in:
+    B200MM_CHECK_SHAPES=1 raises here instead."""
+    if os.environ.get("B200MM_CHECK_SHAPES", "0") in ("", "0"):
+        return
+    mine = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+    world = dist.get_world_size(group)
+    out = torch.empty(world, dtype=torch.int64, device=x.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    sizes = [int(v) for v in out.tolist()]
+    if len(set(sizes)) > 1:
+        raise ValueError(f"b200mm contrastive: ranks hold different numbers of pairs {sizes}; the sharded losses need equal per-rank batches "
+                         "(drop_last=True or a DistributedSampler); use gather_tensor(pad_tensors=True) + a local loss for ragged batches")
+
+
 def _gather_rows(x, group, pad_to=8):
     """[B, E] -> ([Bg_pad, E] all ranks' rows in rank order, zero rows appended up to a multiple of `pad_to`), Bg."""
     rank, world = _world(group)
     B, E = x.shape
+    if world > 1:
+        _check_equal_rows(x, group)
     Bg = B * world
     Bg_pad = (Bg + pad_to - 1) // pad_to * pad_to
     if world == 1 and Bg_pad == Bg:

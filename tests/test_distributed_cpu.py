@@ -227,6 +227,17 @@ WORKER_LOSSES = textwrap.dedent(
             assert abs(mean_over_ranks(loss) - float(full)) < 2e-4 * float(full), (n, float(loss), float(full))
             assert rel(v_loc.grad.float() / world, Vf.grad[rank * B * n:(rank + 1) * B * n]) < 3e-2, n
             assert rel(t_loc.grad.float() / world, Tf.grad[sl]) < 3e-2, n
+    # opt-in guard: ranks with different numbers of pairs raise (on every rank) instead of corrupting / hanging the all-gather
+    os.environ["B200MM_CHECK_SHAPES"] = "1"
+    try:
+        with emulated_ops.patched():
+            n_bad = B + rank
+            clip_contrastive_loss(torch.randn(n_bad, E).to(BF), torch.randn(n_bad, E).to(BF), torch.tensor(2.0))
+        raise AssertionError("unequal per-rank batches must raise under B200MM_CHECK_SHAPES=1")
+    except ValueError as e:
+        assert "different numbers of pairs" in str(e), e
+    finally:
+        os.environ["B200MM_CHECK_SHAPES"] = "0"
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok3_{rank}"), "w").write("ok")
